@@ -1,0 +1,183 @@
+/*
+ * pz.h -- C-ABI of the B200-native Newman-Ziff bond-percolation hot path.
+ *
+ * The reference (andsor/pypercolate) is pure Python and has NO plugin / FFI
+ * layer: its boundary is the Python function surface of percolate/hpc.py and
+ * percolate/percolate.py.  This header is the boundary a maintainer would
+ * bind (ctypes stub in INTEGRATION.md); every entry point names the reference
+ * function whose work it replaces (paths relative to the reference checkout).
+ *
+ * Conventions: plain pointers and sizes, caller-owned buffers, no torch
+ * types.  Every call returns 0 on success or a negative pz_status; the
+ * message of the last failure on the calling thread is pz_last_error().
+ * A context owns one CUDA device, one stream and its scratch; calls on one
+ * context are not re-entrant.  "host" pointers may be pageable or pinned.
+ */
+#ifndef PZ_H
+#define PZ_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pz_ctx pz_ctx;
+
+enum pz_status {
+    PZ_OK = 0,
+    PZ_ERR_ARG = -1,       /* bad argument                                  */
+    PZ_ERR_CUDA = -2,      /* CUDA runtime failure (message has the detail)  */
+    PZ_ERR_STATE = -3,     /* call order (no graph set, nothing accumulated) */
+    PZ_ERR_NOMEM = -4
+};
+
+/* how the bond order of a run is obtained (percolate/hpc.py:195,206) */
+enum pz_perm_mode {
+    PZ_PERM_HOST = 0,      /* caller supplies int32 perms[R][M] (exact mode)             */
+    PZ_PERM_DEVICE = 1,    /* same layout, pointer is device memory                      */
+    PZ_PERM_MT19937 = 2,   /* uint32 seeds[R]; numpy RandomState(seed).permutation(M)
+                              reproduced on the device bit for bit                      */
+    PZ_PERM_PHILOX = 3     /* uint32 seeds[R]; Philox4x32-10 bucketed Fisher-Yates       */
+};
+
+/* number of 64-bit words per bond count n in the micro accumulators */
+#define PZ_ACC_WORDS 20
+/* columns of a per-run canonical statistics row: P_span, max, moments[5] */
+#define PZ_CANON_COLS 7
+
+const char *pz_last_error(void);
+int pz_version(void);
+
+/* ---- context ------------------------------------------------------------ */
+int pz_create(int device, pz_ctx **out);
+void pz_destroy(pz_ctx *ctx);
+int pz_device(const pz_ctx *ctx);
+/* the CUDA stream (cudaStream_t as void*) all work of this context runs on */
+void *pz_stream(const pz_ctx *ctx);
+int pz_synchronize(pz_ctx *ctx);
+
+/*
+ * Upload the lowered graph: replaces the per-bond walks over
+ * ``perc_graph.edges()`` / ``nodes_iter()`` and the auxiliary-node set-up of
+ * bond_sample_states (percolate/hpc.py:205, 224-246).
+ *   eu, ev      host int32[M], endpoints of bond e in perc_graph.edges() order
+ *   side_mask   host uint8[N] (bit s: node touches spanning side s) or NULL
+ *               for spanning_cluster=False
+ *   preconnected  auxiliary structure alone joins both sides
+ */
+int pz_set_graph(pz_ctx *ctx, int32_t N, int32_t M, const int32_t *eu,
+                 const int32_t *ev, const uint8_t *side_mask, int preconnected);
+
+/* bytes of one packed microcanonical_statistics_dtype row
+ * (percolate/hpc.py:57-70): 53 with spanning, 52 without */
+int pz_row_bytes(const pz_ctx *ctx);
+
+/*
+ * R complete runs, materialised: replaces bond_sample_states /
+ * bond_microcanonical_statistics (percolate/hpc.py:73-307, 310-404) and feeds
+ * sample_states / single_run_arrays (percolate/percolate.py:103-447).
+ *   perm_mode, perm_src   see pz_perm_mode
+ *   rows_out   host, R * (M+1) * pz_row_bytes() bytes, packed rows; row 0 of
+ *              each run has edge = 0 (undefined in the reference)
+ *   perms_out  optional host int32[R][M]: the bond orders used (device RNG modes)
+ */
+int pz_run_rows(pz_ctx *ctx, int32_t R, int perm_mode, const void *perm_src,
+                void *rows_out, int32_t *perms_out);
+
+/*
+ * Fused path: R runs are swept and folded, on the device, into
+ *  (a) exact per-n integer sums over runs (micro accumulators) -- the inputs of
+ *      _microcanonical_average_* (percolate/percolate.py:450-705), and/or
+ *  (b) per-run canonical statistics sum_n f_p[n] Q[n]
+ *      (bond_canonical_statistics, percolate/hpc.py:443-515) reduced over runs
+ *      to (count, mean, M2) (bond_initialize_canonical_averages + bond_reduce,
+ *      percolate/hpc.py:561-702).
+ * Nothing per-run leaves the device.  Accumulators persist in the context
+ * until pz_reset_accumulators(); successive calls add runs.
+ *   flags  bit 0: accumulate (a);  bit 1: accumulate (b) (needs pz_set_ps first)
+ */
+#define PZ_FUSE_MICRO 1
+#define PZ_FUSE_CANON 2
+int pz_run_fused(pz_ctx *ctx, int32_t R, int perm_mode, const void *perm_src,
+                 int flags);
+int pz_reset_accumulators(pz_ctx *ctx);
+
+/*
+ * Micro accumulators: for n = 0..M, PZ_ACC_WORDS uint64 words
+ *   [0] runs with a spanning cluster        [1] sum max      [2] sum max^2
+ *   [3] sum c   [4] sum c^2   (c = merges so far; moments[0] = N-1-c)
+ *   [5+5j .. 9+5j], j = 0,1,2 for moments[2+j] = m:
+ *       sum m as two 64-bit limbs (lo, hi), sum m^2 as three limbs (lo, mid, hi)
+ * (moments[1] = N - max needs no words of its own).
+ * pz_micro_runs: number of runs folded so far.
+ * The export/import pair moves the block to/from caller memory (host, or
+ * device when is_device != 0) so that ranks can all-reduce it (plain integer
+ * sum per word is NOT valid across limbs: use pz_micro_export_limbs32).
+ */
+int64_t pz_micro_runs(const pz_ctx *ctx);
+int pz_micro_export(pz_ctx *ctx, uint64_t *dst, int is_device);
+/* the same sums re-expressed so that a word-wise integer all-reduce (sum) over
+ * ranks is exact: every limb is split into 32-bit halves held in 64-bit words.
+ * Layout: (M+1) * PZ_ACC_LIMB32_WORDS words. */
+#define PZ_ACC_LIMB32_WORDS 35
+int pz_micro_export_limbs32(pz_ctx *ctx, uint64_t *dst, int is_device);
+int pz_micro_import_limbs32(pz_ctx *ctx, const uint64_t *src, int is_device, int64_t runs);
+
+/*
+ * Per-n means and sample variances from the exact sums (float64), i.e. the
+ * arithmetic of percolate/percolate.py:557-563, 613-620, 681-690 before the
+ * scipy quantile calls:
+ *   mean_out  host double[7][M+1]: spanning count k, max, moments[0..4]
+ *   var_out   host double[6][M+1]: unbiased variance (ddof=1) of max, moments[0..4];
+ *             exactly 0.0 when all runs agree
+ */
+int pz_micro_finalize(pz_ctx *ctx, double *mean_out, double *var_out);
+
+/*
+ * Binomial weights: replaces _binomial_pmf (percolate/percolate.py:1067-1109),
+ * one p per thread, the reference's mode-outward ratio recurrence in the
+ * reference's operation order.  pmf_out: host double[num_p][M+1] (may be NULL
+ * to keep the table on the device only, for pz_convolve / PZ_FUSE_CANON).
+ */
+int pz_set_ps(pz_ctx *ctx, int32_t num_p, const double *ps, double *pmf_out);
+
+/*
+ * out[c][p] = sum_n pmf_p[n] * cols[c][n]: the contraction of canonical_averages
+ * (percolate/percolate.py:1196-1221) and of bond_canonical_statistics
+ * (percolate/hpc.py:488-515) for host-resident columns.
+ *   cols  host double[num_cols][M+1];  out  host double[num_cols][num_p]
+ */
+int pz_convolve(pz_ctx *ctx, int32_t num_cols, const double *cols, double *out);
+
+/*
+ * bond_canonical_statistics for one materialised run (percolate/hpc.py:443-515):
+ *   rows  host packed rows of ONE run ((M+1) * pz_row_bytes());
+ *   f     host double[M+1] convolution factors;  out  host double[PZ_CANON_COLS]
+ *         (out[0] = percolation probability, 0 when spanning is off)
+ */
+int pz_canonical_statistics_rows(pz_ctx *ctx, const void *rows, const double *f,
+                                 double *out);
+
+/*
+ * Canonical accumulators of the fused path (PZ_FUSE_CANON), the state of
+ * bond_reduce (percolate/hpc.py:638-702):
+ *   count_out  runs folded;  mean_out, m2_out  host double[num_p][PZ_CANON_COLS]
+ * Import merges another partial (Chan et al.) into the context -- the
+ * cross-GPU step.
+ */
+int pz_canon_export(pz_ctx *ctx, int64_t *count_out, double *mean_out, double *m2_out);
+int pz_canon_merge(pz_ctx *ctx, int64_t count, const double *mean, const double *m2);
+
+/* per-run canonical statistics of the LAST pz_run_fused(PZ_FUSE_CANON) call:
+ * host double[R][num_p][PZ_CANON_COLS] (parity tests, small R) */
+int pz_canon_last_runs(pz_ctx *ctx, double *out);
+
+/* number of kernels this context has launched since creation */
+int64_t pz_launch_count(const pz_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PZ_H */

@@ -1,0 +1,461 @@
+// pz_stats.cu -- everything downstream of the merge records (sm_100a).
+//
+// expand_rows      records -> packed microcanonical_statistics_dtype rows
+//                  (percolate/hpc.py:57-70; the per-bond bookkeeping of
+//                  hpc.py:249-307 re-expressed as a block-wide prefix scan)
+#include "pz_common.cuh"
+#include "pz_internal.h"
+
+namespace pz {
+
+// ---------------------------------------------------------------------------
+// block-wide inclusive scan of the run statistics deltas
+// ---------------------------------------------------------------------------
+struct Delta {
+    uint32_t c, mx;
+    uint64_t s2, s3, s4;
+};
+
+__device__ __forceinline__ Delta delta_combine(const Delta &a, const Delta &b) {
+    Delta r;
+    r.c = a.c + b.c;
+    r.mx = a.mx > b.mx ? a.mx : b.mx;
+    r.s2 = a.s2 + b.s2; r.s3 = a.s3 + b.s3; r.s4 = a.s4 + b.s4;
+    return r;
+}
+__device__ __forceinline__ Delta delta_shfl_up(const Delta &d, int k) {
+    Delta r;
+    r.c = __shfl_up_sync(0xffffffffu, d.c, k);
+    r.mx = __shfl_up_sync(0xffffffffu, d.mx, k);
+    r.s2 = __shfl_up_sync(0xffffffffu, d.s2, k);
+    r.s3 = __shfl_up_sync(0xffffffffu, d.s3, k);
+    r.s4 = __shfl_up_sync(0xffffffffu, d.s4, k);
+    return r;
+}
+template <class RecT>
+__device__ __forceinline__ Delta delta_of(RecT r) {
+    Delta d{0, 0, 0, 0, 0};
+    if (RecCodec<RecT>::valid(r)) {
+        const uint64_t a = RecCodec<RecT>::w_small(r), b = RecCodec<RecT>::w_large(r), w = a + b;
+        const uint64_t a2 = a * a, b2 = b * b, w2 = w * w;
+        d.c = 1; d.mx = (uint32_t)w;
+        d.s2 = w2 - a2 - b2;
+        d.s3 = w2 * w - a2 * a - b2 * b;
+        d.s4 = w2 * w2 - a2 * a2 - b2 * b2;
+    }
+    return d;
+}
+
+static constexpr int ROWS_THREADS = 256;
+
+template <int BYTE_OFF>
+__device__ __forceinline__ void put32(uint32_t (&w)[14], uint32_t v) {
+    constexpr int i = BYTE_OFF / 4, s = (BYTE_OFF % 4) * 8;
+    w[i] |= v << s;
+    if constexpr (s != 0) w[i + 1] |= v >> ((32 - s) & 31);
+}
+template <int BYTE_OFF>
+__device__ __forceinline__ void put64(uint32_t (&w)[14], uint64_t v) {
+    put32<BYTE_OFF>(w, (uint32_t)v);
+    put32<BYTE_OFF + 4>(w, (uint32_t)(v >> 32));
+}
+
+// one CTA per run; rows 0..M in chunks of ROWS_THREADS
+template <class RecT, bool SPANNING>
+__global__ void __launch_bounds__(ROWS_THREADS) expand_rows_kernel(StatsArgs a, uint8_t *rows)
+{
+    constexpr int RB = SPANNING ? 53 : 52;
+    __shared__ Delta warp_tot[ROWS_THREADS / 32];
+    __shared__ Delta carry;
+    __shared__ __align__(16) uint8_t stage[ROWS_THREADS * RB + 8];
+
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int run = blockIdx.x;
+    const RecT *recs = reinterpret_cast<const RecT *>(a.recs) + (size_t)run * a.M;
+    const int32_t *perm = a.perms ? a.perms + (size_t)run * a.M : nullptr;
+    const uint32_t nspan = a.nspan[run];
+    const int rows_total = a.M + 1;
+    if (t == 0) carry = Delta{0u, 1u, (uint64_t)a.N, (uint64_t)a.N, (uint64_t)a.N};   // n = 0: c = 0, max = 1, S_k = N
+    __syncthreads();
+
+    for (int n0 = 0; n0 < rows_total; n0 += ROWS_THREADS) {
+        const int n = n0 + t;
+        const bool valid = n < rows_total;
+        Delta d{0, 0, 0, 0, 0};
+        if (valid && n >= 1) d = delta_of<RecT>(recs[n - 1]);
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) {
+            Delta o = delta_shfl_up(d, k);
+            if (lane >= k) d = delta_combine(o, d);
+        }
+        if (lane == 31) warp_tot[warp] = d;
+        __syncthreads();
+        Delta pre = carry;
+        for (int w = 0; w < warp; ++w) pre = delta_combine(pre, warp_tot[w]);
+        d = delta_combine(pre, d);
+        __syncthreads();
+        if (t == ROWS_THREADS - 1) carry = d;
+
+        const int nrows = min(ROWS_THREADS, rows_total - n0);
+        const size_t goff = ((size_t)run * rows_total + n0) * RB;
+        const int shift = (int)(goff & 3);
+        if (valid) {
+            uint32_t w[14];
+#pragma unroll
+            for (int i = 0; i < 14; ++i) w[i] = 0;
+            const uint64_t x = d.mx, x2 = x * x;
+            w[0] = (uint32_t)n;
+            w[1] = (n >= 1 && perm) ? (uint32_t)perm[n - 1] : 0u;
+            if (SPANNING) {
+                w[2] = (uint32_t)n >= nspan ? 1u : 0u;
+                put32<9>(w, d.mx);
+                put64<13>(w, (uint64_t)a.N - 1 - d.c);
+                put64<21>(w, (uint64_t)a.N - x);
+                put64<29>(w, d.s2 - x2);
+                put64<37>(w, d.s3 - x2 * x);
+                put64<45>(w, d.s4 - x2 * x2);
+            } else {
+                put32<8>(w, d.mx);
+                put64<12>(w, (uint64_t)a.N - 1 - d.c);
+                put64<20>(w, (uint64_t)a.N - x);
+                put64<28>(w, d.s2 - x2);
+                put64<36>(w, d.s3 - x2 * x);
+                put64<44>(w, d.s4 - x2 * x2);
+            }
+            uint8_t *dst = stage + shift + t * RB;
+#pragma unroll
+            for (int i = 0; i < RB; ++i) dst[i] = (uint8_t)(w[i / 4] >> ((i % 4) * 8));
+        }
+        __syncthreads();
+        // coalesced copy-out: head bytes, aligned words, tail bytes
+        {
+            const int total = nrows * RB;
+            const int head = min((4 - shift) & 3, total);
+            uint8_t *g = rows + goff;
+            const uint8_t *s = stage + shift;
+            if (t < head) g[t] = s[t];
+            const int nwords = (total - head) / 4;
+            const uint32_t *s32 = reinterpret_cast<const uint32_t *>(s + head);
+            uint32_t *g32 = reinterpret_cast<uint32_t *>(g + head);
+            for (int i = t; i < nwords; i += ROWS_THREADS) g32[i] = s32[i];
+            const int done = head + nwords * 4;
+            if (t < total - done) g[done + t] = s[done + t];
+        }
+        __syncthreads();
+    }
+}
+
+
+// ===========================================================================
+// accumulate: per-n exact integer sums over runs (the inputs of
+// _microcanonical_average_*, percolate/percolate.py:450-705).
+//
+// One lane owns one run and walks its records in n; a warp therefore advances
+// 32 runs in lock step.  Records are staged through a padded shared-memory
+// tile so that global reads are 128-byte coalesced and the per-lane walk is
+// bank-conflict free.  For every row the 25 accumulator words of the 32 runs
+// are summed with a recursive-halving exchange (31 64-bit shuffles; lane w
+// ends up holding the warp total of word w) and added to the global
+// accumulators with one 64-bit atomic per word per warp.
+//
+// Accumulator words per n (all uint64; 32-bit limbs so that word-wise integer
+// sums over any number of partials -- warps here, GPUs in the all-reduce --
+// are exact):
+//   0        runs whose spanning cluster FIRST appears at n (delta form)
+//   1        sum max           2,3    sum max^2      (lo32, hi32)
+//   4        sum c             5,6    sum c^2        (c = merges so far)
+//   7+6j..   j = 0,1,2 for moments[2+j] = m:
+//            sum m (lo32, hi32), sum m^2 (four 32-bit limbs)
+// Optionally writes the run state every CKPT rows (used by the per-run
+// canonical contraction to start in the middle of a run).
+// ===========================================================================
+static constexpr int ACC_WORDS = 25;
+
+template <int HALF>
+__device__ __forceinline__ void halve_step(uint64_t (&v)[32], int lane) {
+    const bool up = lane & HALF;
+#pragma unroll
+    for (int i = 0; i < HALF; ++i) {
+        const uint64_t send = up ? v[i] : v[i + HALF];
+        const uint64_t keep = up ? v[i + HALF] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, HALF);
+    }
+}
+
+template <class RecT, bool ACCUM>
+__global__ void __launch_bounds__(256) accumulate_kernel(StatsArgs a, unsigned long long *acc,
+                                                          RunState *ckpt, int ckpt_every, int n_ckpt)
+{
+    constexpr int TILE = sizeof(RecT) == 4 ? 32 : 16;
+    __shared__ RecT tile_all[8][32][TILE + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    RecT (*tile)[TILE + 1] = tile_all[warp];
+    const int run0 = (blockIdx.x * 8 + warp) * 32;
+    if (run0 >= a.R) return;
+    const int run = run0 + lane;
+    const bool live = run < a.R;
+    const RecT *recs = reinterpret_cast<const RecT *>(a.recs);
+    const int M = a.M;
+
+    RunState st;
+    st.init((uint32_t)a.N);
+    if (ACCUM && live && a.spanning) {
+        const uint32_t ns = a.nspan[run];
+        if (ns != NSPAN_NEVER) atomicAdd(&acc[(size_t)ns * ACC_WORDS + 0], 1ull);
+    }
+
+    // rows n = 0..M; row n >= 1 applies record n-1
+    for (int r0 = 0; r0 <= M; r0 += TILE) {
+        // stage records r0-1 .. r0+TILE-2 of the 32 runs
+        __syncwarp();
+        if (lane < TILE) {
+            const int idx = r0 - 1 + lane;
+            for (int rr = 0; rr < 32; ++rr) {
+                RecT v = 0;
+                if (run0 + rr < a.R && idx >= 0 && idx < M)
+                    v = __ldcs(&recs[(size_t)(run0 + rr) * M + idx]);
+                tile[rr][lane] = v;
+            }
+        }
+        __syncwarp();
+        const int rows = min(TILE, M + 1 - r0);
+        for (int j = 0; j < rows; ++j) {
+            const int n = r0 + j;
+            const RecT r = tile[lane][j];
+            if (RecCodec<RecT>::valid(r)) st.merge(RecCodec<RecT>::w_small(r), RecCodec<RecT>::w_large(r));
+            if (ckpt && live && (n % ckpt_every) == 0)
+                ckpt[(size_t)run * n_ckpt + n / ckpt_every] = st;
+            if (ACCUM) {
+                uint64_t v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0;
+                if (live) {
+                    const uint64_t x = st.mx, x2 = x * x, c = st.c, c2 = c * c;
+                    v[1] = x;
+                    v[2] = x2 & 0xffffffffu; v[3] = x2 >> 32;
+                    v[4] = c;
+                    v[5] = c2 & 0xffffffffu; v[6] = c2 >> 32;
+                    const uint64_t m[3] = {st.s2 - x2, st.s3 - x2 * x, st.s4 - x2 * x2};
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const uint64_t lo = m[k] * m[k], hi = __umul64hi(m[k], m[k]);
+                        v[7 + 6 * k + 0] = m[k] & 0xffffffffu;
+                        v[7 + 6 * k + 1] = m[k] >> 32;
+                        v[7 + 6 * k + 2] = lo & 0xffffffffu;
+                        v[7 + 6 * k + 3] = lo >> 32;
+                        v[7 + 6 * k + 4] = hi & 0xffffffffu;
+                        v[7 + 6 * k + 5] = hi >> 32;
+                    }
+                }
+                halve_step<16>(v, lane);
+                halve_step<8>(v, lane);
+                halve_step<4>(v, lane);
+                halve_step<2>(v, lane);
+                halve_step<1>(v, lane);
+                if (lane >= 1 && lane < ACC_WORDS && v[0])
+                    atomicAdd(&acc[(size_t)n * ACC_WORDS + lane], (unsigned long long)v[0]);
+            }
+        }
+    }
+}
+
+cudaError_t launch_accumulate(const StatsArgs &a, unsigned long long *acc, RunState *ckpt,
+                              int ckpt_every, int n_ckpt, cudaStream_t s)
+{
+    if (a.R <= 0) return cudaSuccess;
+    const int grid = (a.R + 255) / 256;
+    if (acc) {
+        if (a.rec64) accumulate_kernel<uint64_t, true><<<grid, 256, 0, s>>>(a, acc, ckpt, ckpt_every, n_ckpt);
+        else accumulate_kernel<uint32_t, true><<<grid, 256, 0, s>>>(a, acc, ckpt, ckpt_every, n_ckpt);
+    } else {
+        if (a.rec64) accumulate_kernel<uint64_t, false><<<grid, 256, 0, s>>>(a, acc, ckpt, ckpt_every, n_ckpt);
+        else accumulate_kernel<uint32_t, false><<<grid, 256, 0, s>>>(a, acc, ckpt, ckpt_every, n_ckpt);
+    }
+    return cudaGetLastError();
+}
+
+// ===========================================================================
+// micro_finalize: exact sums -> float64 mean and unbiased variance per n.
+// var = (R * sum x^2 - (sum x)^2) / (R (R-1)) is formed in 256-bit integer
+// arithmetic, so it is exactly 0 when all runs agree (the reference's
+// ``if std:`` branches, percolate/percolate.py:621-633, 691-703) and carries
+// no cancellation error otherwise.
+// ===========================================================================
+struct U256 {
+    uint64_t w[4];
+};
+__device__ __forceinline__ U256 u256_zero() { U256 r; r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0; return r; }
+__device__ __forceinline__ void u256_add_shifted(U256 &x, uint64_t v, int bit) {
+    // x += v << bit   (bit multiple of 32)
+    const int limb = bit >> 6, sh = bit & 63;
+    uint64_t lo = v << sh, hi = sh ? (v >> (64 - sh)) : 0;
+    unsigned carry = 0;
+    for (int i = limb; i < 4; ++i) {
+        const uint64_t add = (i == limb ? lo : (i == limb + 1 ? hi : 0));
+        const uint64_t s1 = x.w[i] + add;
+        const unsigned c1 = s1 < add;
+        const uint64_t s2 = s1 + carry;
+        const unsigned c2 = s2 < s1;
+        x.w[i] = s2;
+        carry = c1 | c2;
+    }
+}
+__device__ __forceinline__ U256 u256_mul64(const U256 &x, uint64_t m) {
+    U256 r = u256_zero();
+    uint64_t carry = 0;
+    for (int i = 0; i < 4; ++i) {
+        const uint64_t lo = x.w[i] * m, hi = __umul64hi(x.w[i], m);
+        const uint64_t s = lo + carry;
+        r.w[i] = s;
+        carry = hi + (s < lo);
+    }
+    return r;
+}
+__device__ __forceinline__ U256 u256_sqr128(uint64_t a0, uint64_t a1) {
+    // (a0 + a1 2^64)^2
+    U256 r = u256_zero();
+    r.w[0] = a0 * a0; r.w[1] = __umul64hi(a0, a0);
+    const uint64_t clo = a0 * a1, chi = __umul64hi(a0, a1);
+    // 2 * cross << 64
+    U256 cross = u256_zero();
+    cross.w[1] = clo << 1; cross.w[2] = (chi << 1) | (clo >> 63); cross.w[3] = chi >> 63;
+    U256 top = u256_zero();
+    top.w[2] = a1 * a1; top.w[3] = __umul64hi(a1, a1);
+    unsigned carry = 0;
+    for (int i = 0; i < 4; ++i) {
+        uint64_t s = r.w[i] + cross.w[i]; unsigned c1 = s < cross.w[i];
+        uint64_t s2 = s + top.w[i]; unsigned c2 = s2 < top.w[i];
+        uint64_t s3 = s2 + carry; unsigned c3 = s3 < s2;
+        r.w[i] = s3; carry = c1 + c2 + c3;
+    }
+    return r;
+}
+__device__ __forceinline__ U256 u256_sub(const U256 &a, const U256 &b) {
+    U256 r; unsigned borrow = 0;
+    for (int i = 0; i < 4; ++i) {
+        const uint64_t d = a.w[i] - b.w[i]; const unsigned b1 = a.w[i] < b.w[i];
+        const uint64_t d2 = d - borrow; const unsigned b2 = d < borrow;
+        r.w[i] = d2; borrow = b1 | b2;
+    }
+    return r;
+}
+__device__ __forceinline__ double u256_to_double(const U256 &x) {
+    int top = 3;
+    while (top > 0 && x.w[top] == 0) --top;
+    if (top == 0) return (double)x.w[0];
+    const double hi = (double)x.w[top], lo = (double)x.w[top - 1];
+    return ldexp(hi * 18446744073709551616.0 + lo, 64 * (top - 1));
+}
+// sum x as (lo32-word, hi32-word) -> 128-bit
+__device__ __forceinline__ void sum128(uint64_t wlo, uint64_t whi, uint64_t &a0, uint64_t &a1) {
+    U256 t = u256_zero();
+    u256_add_shifted(t, wlo, 0);
+    u256_add_shifted(t, whi, 32);
+    a0 = t.w[0]; a1 = t.w[1];
+}
+__device__ __forceinline__ double var_exact(uint64_t a0, uint64_t a1, const U256 &B, uint64_t R) {
+    if (R < 2) return nan("");
+    const U256 RB = u256_mul64(B, R);
+    const U256 A2 = u256_sqr128(a0, a1);
+    const U256 D = u256_sub(RB, A2);
+    return u256_to_double(D) / ((double)R * (double)(R - 1));
+}
+__device__ __forceinline__ double mean_exact(uint64_t a0, uint64_t a1, uint64_t R) {
+    U256 t = u256_zero(); t.w[0] = a0; t.w[1] = a1;
+    return u256_to_double(t) / (double)R;
+}
+
+// mean[7][M+1]: spanning count, max, moments 0..4 ; var[6][M+1]: max, moments 0..4
+__global__ void micro_finalize_kernel(int32_t N, int32_t M, unsigned long long R,
+                                      const unsigned long long *acc,
+                                      const unsigned long long *span_cum, double *mean, double *var)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n > M) return;
+    const unsigned long long *w = acc + (size_t)n * ACC_WORDS;
+    const size_t S = (size_t)M + 1;
+    mean[0 * S + n] = (double)span_cum[n];
+    // max
+    {
+        uint64_t b0, b1; sum128(w[2], w[3], b0, b1);
+        U256 B = u256_zero(); B.w[0] = b0; B.w[1] = b1;
+        mean[1 * S + n] = mean_exact(w[1], 0, R);
+        const double v = var_exact(w[1], 0, B, R);
+        var[0 * S + n] = v;
+        // moments[1] = N - max  (percolate/hpc.py:214, 283-305)
+        const uint64_t s1 = (uint64_t)N * R - w[1];
+        mean[3 * S + n] = mean_exact(s1, 0, R);
+        var[2 * S + n] = v;
+    }
+    // moments[0] = N - 1 - c
+    {
+        uint64_t b0, b1; sum128(w[5], w[6], b0, b1);
+        U256 B = u256_zero(); B.w[0] = b0; B.w[1] = b1;
+        const uint64_t s0 = (uint64_t)(N - 1) * R - w[4];
+        mean[2 * S + n] = mean_exact(s0, 0, R);
+        var[1 * S + n] = var_exact(w[4], 0, B, R);
+    }
+    for (int k = 0; k < 3; ++k) {
+        const unsigned long long *q = w + 7 + 6 * k;
+        uint64_t a0, a1; sum128(q[0], q[1], a0, a1);
+        U256 B = u256_zero();
+        u256_add_shifted(B, q[2], 0);
+        u256_add_shifted(B, q[3], 32);
+        u256_add_shifted(B, q[4], 64);
+        u256_add_shifted(B, q[5], 96);
+        mean[(4 + k) * S + n] = mean_exact(a0, a1, R);
+        var[(3 + k) * S + n] = var_exact(a0, a1, B, R);
+    }
+}
+
+// inclusive prefix sum of word 0 (delta form -> runs spanning at n); one CTA
+__global__ void span_cumsum_kernel(int32_t M, const unsigned long long *acc, unsigned long long *out)
+{
+    __shared__ unsigned long long warp_tot[32];
+    __shared__ unsigned long long carry;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0) carry = 0;
+    __syncthreads();
+    for (int n0 = 0; n0 <= M; n0 += 1024) {
+        const int n = n0 + t;
+        unsigned long long v = n <= M ? acc[(size_t)n * ACC_WORDS] : 0ull;
+        for (int k = 1; k < 32; k <<= 1) {
+            const unsigned long long o = __shfl_up_sync(0xffffffffu, v, k);
+            if (lane >= k) v += o;
+        }
+        if (lane == 31) warp_tot[warp] = v;
+        __syncthreads();
+        unsigned long long pre = carry;
+        for (int w = 0; w < warp; ++w) pre += warp_tot[w];
+        v += pre;
+        if (n <= M) out[n] = v;
+        __syncthreads();
+        if (t == 1023) carry = v;
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_micro_finalize(int32_t N, int32_t M, int64_t runs, const unsigned long long *acc,
+                                  unsigned long long *span_cum, double *mean, double *var,
+                                  cudaStream_t s)
+{
+    span_cumsum_kernel<<<1, 1024, 0, s>>>(M, acc, span_cum);
+    const int grid = (M + 1 + 127) / 128;
+    micro_finalize_kernel<<<grid, 128, 0, s>>>(N, M, (unsigned long long)runs, acc, span_cum, mean, var);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_expand_rows(const StatsArgs &a, uint8_t *rows, cudaStream_t s)
+{
+    if (a.R <= 0) return cudaSuccess;
+    if (a.rec64) {
+        if (a.spanning) expand_rows_kernel<uint64_t, true><<<a.R, ROWS_THREADS, 0, s>>>(a, rows);
+        else expand_rows_kernel<uint64_t, false><<<a.R, ROWS_THREADS, 0, s>>>(a, rows);
+    } else {
+        if (a.spanning) expand_rows_kernel<uint32_t, true><<<a.R, ROWS_THREADS, 0, s>>>(a, rows);
+        else expand_rows_kernel<uint32_t, false><<<a.R, ROWS_THREADS, 0, s>>>(a, rows);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace pz

@@ -1,0 +1,403 @@
+// pz_sweep.cu -- the per-run union-find sweep (sm_100a).
+//
+// Replaces the hot loop of the reference, percolate/hpc.py:249-307 (twin:
+// percolate/percolate.py:298-356): one Python iteration per bond over a dict
+// union-find.  Here ONE WARP owns one run and adds bonds 32 at a time:
+//
+//   1. every lane looks up the endpoints of its bond and finds both roots in
+//      parallel (weighted quick-union, path halving).  Concurrent halving
+//      writes are benign: they only ever replace a parent by an ancestor.
+//   2. lanes whose roots differ are merge candidates.  A candidate may merge
+//      immediately iff no LOWER lane touches either of its roots: then every
+//      earlier bond of the batch works on disjoint clusters, so the sizes it
+//      sees are exactly the ones the sequential reference sees.  This is
+//      decided with one atomicMin claim per root in a hashed shared-memory
+//      table (hash collisions only delay a lane, never break the order).
+//   3. what is left (chains through a common cluster, typically the giant
+//      one) is replayed in bond order, the whole warp walking together.
+//
+// The parent/size array of the run lives in shared memory whenever it fits
+// (uint16 entries; N <= 65536 covers the L = 256 square lattice in 136 KB),
+// otherwise in a per-warp slab of global memory that stays L2-resident.
+// Output per bond is one merge record (see pz_common.cuh); per run one word,
+// the first n at which the two spanning sides are joined (hpc.py:269-274).
+#include "pz_common.cuh"
+#include "pz_internal.h"
+
+namespace pz {
+
+static constexpr uint32_t CLAIM_FREE = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
+static inline size_t align16h(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// ---------------------------------------------------------------------------
+// Stores.  Common surface:
+//   init(lane)                 every node its own cluster of size 1
+//   find(x, tok) -> root       tok = opaque root token (carries size-1)
+//   size_m1(tok)
+//   unite(ra, ta, rb, tb, track) -> side mask of the merged cluster (0 if !track)
+// ---------------------------------------------------------------------------
+struct StoreS16 {
+    using Rec = uint32_t;
+    using Edge = uint32_t;
+    uint16_t *val;        // bit 15: root; low 15 bits: size-1 (root) or parent
+    uint32_t *sides2;     // 2-bit side fields
+    int32_t N;
+    const uint32_t *sides_init;
+
+    static size_t slice_bytes(int32_t N) {
+        return align16h((size_t)N * 2) + align16h((size_t)((N + 15) / 16) * 4);
+    }
+    __device__ void bind(unsigned char *slice, const SweepArgs &a, int) {
+        N = a.N;
+        val = reinterpret_cast<uint16_t *>(slice);
+        sides2 = reinterpret_cast<uint32_t *>(slice + align16((uint32_t)N * 2));
+        sides_init = a.sides2;
+    }
+    __device__ void init(int lane) {
+        uint32_t *v32 = reinterpret_cast<uint32_t *>(val);
+        for (int i = lane; i < (N + 1) / 2; i += 32) v32[i] = 0x80008000u;
+        if (sides_init)
+            for (int i = lane; i < (N + 15) / 16; i += 32) sides2[i] = sides_init[i];
+    }
+    __device__ __forceinline__ uint32_t find(uint32_t x, uint32_t &tok) const {
+        uint32_t vx = val[x];
+        while (!(vx & 0x8000u)) {
+            const uint32_t p = vx, vp = val[p];
+            if (vp & 0x8000u) { x = p; vx = vp; break; }
+            val[x] = (uint16_t)vp;          // halve: parent[x] = grandparent
+            x = vp;
+            vx = val[x];
+        }
+        tok = vx;
+        return x;
+    }
+    static __device__ __forceinline__ uint32_t size_m1(uint32_t tok) { return tok & 0x7fffu; }
+    __device__ __forceinline__ uint32_t side_of(uint32_t r) const {
+        return (sides2[r >> 4] >> ((r & 15u) * 2)) & 3u;
+    }
+    __device__ __forceinline__ uint32_t unite(uint32_t ra, uint32_t ta, uint32_t rb, uint32_t tb,
+                                              bool track) {
+        const uint32_t sa = size_m1(ta), sb = size_m1(tb);
+        const uint32_t big = sa >= sb ? ra : rb, small = sa >= sb ? rb : ra;
+        val[small] = (uint16_t)big;
+        val[big] = (uint16_t)(0x8000u | (sa + sb + 1));
+        uint32_t m = 0;
+        if (track) {
+            const uint32_t mb = side_of(big);
+            m = mb | side_of(small);
+            if (m != mb) atomicOr(&sides2[big >> 4], m << ((big & 15u) * 2));
+        }
+        return m;
+    }
+};
+
+struct StoreS16B {
+    using Rec = uint32_t;
+    using Edge = uint32_t;
+    uint16_t *val;        // size-1 (root) or parent
+    uint32_t *rootbits;   // bit x: node x is a root
+    uint32_t *sides2;
+    int32_t N;
+    const uint32_t *sides_init;
+
+    static size_t slice_bytes(int32_t N) {
+        return align16h((size_t)N * 2) + align16h((size_t)((N + 31) / 32) * 4) +
+               align16h((size_t)((N + 15) / 16) * 4);
+    }
+    __device__ void bind(unsigned char *slice, const SweepArgs &a, int) {
+        N = a.N;
+        val = reinterpret_cast<uint16_t *>(slice);
+        uint32_t off = align16((uint32_t)N * 2);
+        rootbits = reinterpret_cast<uint32_t *>(slice + off);
+        off += align16((uint32_t)((N + 31) / 32) * 4);
+        sides2 = reinterpret_cast<uint32_t *>(slice + off);
+        sides_init = a.sides2;
+    }
+    __device__ void init(int lane) {
+        uint4 *v128 = reinterpret_cast<uint4 *>(val);
+        const int n128 = (N * 2 + 15) / 16;
+        for (int i = lane; i < n128; i += 32) v128[i] = make_uint4(0, 0, 0, 0);
+        for (int i = lane; i < (N + 31) / 32; i += 32) rootbits[i] = 0xffffffffu;
+        if (sides_init)
+            for (int i = lane; i < (N + 15) / 16; i += 32) sides2[i] = sides_init[i];
+    }
+    __device__ __forceinline__ bool is_root(uint32_t x) const {
+        return (rootbits[x >> 5] >> (x & 31u)) & 1u;
+    }
+    __device__ __forceinline__ uint32_t find(uint32_t x, uint32_t &tok) const {
+        bool rx = is_root(x);
+        uint32_t vx = val[x];
+        while (!rx) {
+            const uint32_t p = vx;
+            const bool rp = is_root(p);
+            const uint32_t vp = val[p];
+            if (rp) { x = p; vx = vp; break; }
+            val[x] = (uint16_t)vp;
+            x = vp;
+            rx = is_root(x);
+            vx = val[x];
+        }
+        tok = vx;
+        return x;
+    }
+    static __device__ __forceinline__ uint32_t size_m1(uint32_t tok) { return tok; }
+    __device__ __forceinline__ uint32_t side_of(uint32_t r) const {
+        return (sides2[r >> 4] >> ((r & 15u) * 2)) & 3u;
+    }
+    __device__ __forceinline__ uint32_t unite(uint32_t ra, uint32_t ta, uint32_t rb, uint32_t tb,
+                                              bool track) {
+        const uint32_t sa = ta, sb = tb;
+        const uint32_t big = sa >= sb ? ra : rb, small = sa >= sb ? rb : ra;
+        val[small] = (uint16_t)big;
+        atomicAnd(&rootbits[small >> 5], ~(1u << (small & 31u)));
+        val[big] = (uint16_t)(sa + sb + 1);
+        uint32_t m = 0;
+        if (track) {
+            const uint32_t mb = side_of(big);
+            m = mb | side_of(small);
+            if (m != mb) atomicOr(&sides2[big >> 4], m << ((big & 15u) * 2));
+        }
+        return m;
+    }
+};
+
+struct StoreG32 {
+    using Rec = uint64_t;
+    using Edge = uint2;
+    uint32_t *val;        // root: bit31 | sides << 29 | size-1 ; else parent
+    int32_t N;
+    const uint32_t *sides_init;
+
+    static size_t slice_bytes(int32_t) { return 0; }
+    __device__ void bind(unsigned char *, const SweepArgs &a, int gwarp) {
+        N = a.N;
+        val = a.gscratch + (size_t)gwarp * (size_t)a.N;
+        sides_init = a.sides2;
+    }
+    __device__ void init(int lane) {
+        for (int i = lane; i < N; i += 32) {
+            uint32_t s = sides_init ? (sides_init[i >> 4] >> ((i & 15) * 2)) & 3u : 0u;
+            val[i] = 0x80000000u | (s << 29);
+        }
+    }
+    __device__ __forceinline__ uint32_t find(uint32_t x, uint32_t &tok) const {
+        uint32_t vx = val[x];
+        while (!(vx >> 31)) {
+            const uint32_t p = vx, vp = val[p];
+            if (vp >> 31) { x = p; vx = vp; break; }
+            val[x] = vp;
+            x = vp;
+            vx = val[x];
+        }
+        tok = vx;
+        return x;
+    }
+    static __device__ __forceinline__ uint32_t size_m1(uint32_t tok) { return tok & 0x1fffffffu; }
+    __device__ __forceinline__ uint32_t unite(uint32_t ra, uint32_t ta, uint32_t rb, uint32_t tb,
+                                              bool) {
+        const uint32_t sa = size_m1(ta), sb = size_m1(tb);
+        const uint32_t big = sa >= sb ? ra : rb, small = sa >= sb ? rb : ra;
+        const uint32_t m = ((ta | tb) >> 29) & 3u;
+        val[small] = big;
+        val[big] = 0x80000000u | (m << 29) | (sa + sb + 1);
+        return m;
+    }
+};
+
+template <class Rec> __device__ __forceinline__ Rec make_rec(uint32_t a, uint32_t b);
+template <> __device__ __forceinline__ uint32_t make_rec<uint32_t>(uint32_t a, uint32_t b) { return rec32_pack(a, b); }
+template <> __device__ __forceinline__ uint64_t make_rec<uint64_t>(uint32_t a, uint32_t b) { return rec64_pack(a, b); }
+
+__device__ __forceinline__ void edge_uv(uint32_t e, uint32_t &u, uint32_t &v) { u = e & 0xffffu; v = e >> 16; }
+__device__ __forceinline__ void edge_uv(uint2 e, uint32_t &u, uint32_t &v) { u = e.x; v = e.y; }
+__device__ __forceinline__ uint32_t claim_slot(uint32_t r, int log2) {
+    return (r * 0x9E3779B1u) >> (32 - log2);
+}
+
+template <class Store>
+__global__ void sweep_kernel(SweepArgs a, uint32_t slice_bytes)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    using Rec = typename Store::Rec;
+    using Edge = typename Store::Edge;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wpc = blockDim.x >> 5;
+    const int gwarp = blockIdx.x * wpc + warp, nwarps = gridDim.x * wpc;
+    const int M = a.M;
+    const int clog = a.claim_log2;
+
+    unsigned char *slice = smem + (size_t)warp * slice_bytes;
+    uint32_t *claim = reinterpret_cast<uint32_t *>(slice);
+    Store st;
+    st.bind(slice + (sizeof(uint32_t) << clog), a, gwarp);
+    for (int i = lane; i < (1 << clog); i += 32) claim[i] = CLAIM_FREE;
+
+    const Edge *edges = reinterpret_cast<const Edge *>(a.edges);
+    const bool spanning = a.sides2 != nullptr;
+
+    for (int run = gwarp; run < a.R; run += nwarps) {
+        st.init(lane);
+        __syncwarp();
+        const int32_t *perm = a.perms + (size_t)run * M;
+        Rec *rec_out = reinterpret_cast<Rec *>(a.recs) + (size_t)run * M;
+        uint32_t nspan = NSPAN_NEVER;
+        bool track = spanning;                 // warp-uniform
+
+        // two-deep software pipeline: perm[n] -> edges[perm[n]] -> use
+        Edge uv_next = Edge();
+        int32_t e_next = 0;
+        if (lane < M) uv_next = __ldg(&edges[__ldcs(&perm[lane])]);
+        if (lane + 32 < M) e_next = __ldcs(&perm[lane + 32]);
+
+        for (int n0 = 0; n0 < M; n0 += 32) {
+            const int n = n0 + lane;           // bond index; row index is n + 1
+            const bool valid = n < M;
+            const Edge uv = uv_next;
+            if (n + 32 < M) uv_next = __ldg(&edges[e_next]);
+            if (n + 64 < M) e_next = __ldcs(&perm[n + 64]);
+
+            uint32_t ru = 0, rv = 0, tu = 0, tv = 0;
+            if (valid) {
+                uint32_t u, v;
+                edge_uv(uv, u, v);
+                ru = st.find(u, tu);
+                rv = st.find(v, tv);
+            }
+            const bool cand = valid && ru != rv;
+            const uint32_t cmask = __ballot_sync(0xffffffffu, cand);
+            Rec rec = 0;
+            if (cmask) {
+                __syncwarp();
+                uint32_t span_n = NSPAN_NEVER;
+                uint32_t remaining = cmask;
+                if (__popc(cmask) > 2) {
+                    // ---- claim round: order-safe parallel merges ---------------
+                    uint32_t su = 0, sv = 0;
+                    if (cand) {
+                        su = claim_slot(ru, clog);
+                        sv = claim_slot(rv, clog);
+                        atomicMin(&claim[su], (uint32_t)lane);
+                        atomicMin(&claim[sv], (uint32_t)lane);
+                    }
+                    __syncwarp();
+                    const bool win = cand && claim[su] == (uint32_t)lane && claim[sv] == (uint32_t)lane;
+                    __syncwarp();
+                    if (cand) { claim[su] = CLAIM_FREE; claim[sv] = CLAIM_FREE; }
+                    if (win) {
+                        rec = make_rec<Rec>(Store::size_m1(tu), Store::size_m1(tv));
+                        const uint32_t m = st.unite(ru, tu, rv, tv, track);
+                        if (track && (m == 3u || a.any3)) span_n = (uint32_t)n + 1;
+                    }
+                    remaining = cmask & ~__ballot_sync(0xffffffffu, win);
+                    __syncwarp();
+                }
+                // ---- replay of the dependent merges in bond order ------------
+                while (remaining) {
+                    const int l = __ffs(remaining) - 1;
+                    remaining &= remaining - 1;
+                    uint32_t ta, tb;
+                    const uint32_t ra = st.find(__shfl_sync(0xffffffffu, ru, l), ta);
+                    const uint32_t rb = st.find(__shfl_sync(0xffffffffu, rv, l), tb);
+                    if (ra != rb) {
+                        // all lanes perform the same (idempotent) writes
+                        const uint32_t m = st.unite(ra, ta, rb, tb, track);
+                        if (lane == l) {
+                            rec = make_rec<Rec>(Store::size_m1(ta), Store::size_m1(tb));
+                            if (track && (m == 3u || a.any3)) span_n = (uint32_t)n + 1;
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (track) {
+                    span_n = __reduce_min_sync(0xffffffffu, span_n);
+                    if (span_n != NSPAN_NEVER) { nspan = span_n; track = false; }
+                }
+            }
+            if (valid) __stcs(&rec_out[n], rec);
+        }
+        if (lane == 0) a.nspan[run] = nspan;
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// planning and launch
+// ---------------------------------------------------------------------------
+static int ilog2_ceil(uint32_t x) { int l = 0; while ((1u << l) < x) ++l; return l; }
+
+SweepPlan plan_sweep(int32_t N, int32_t R, int sms, size_t smem_optin, int force_kind)
+{
+    SweepPlan p{};
+    const size_t budget = smem_optin;          // per CTA (opt-in maximum)
+    StoreKind kind;
+    if (force_kind >= 0) kind = (StoreKind)force_kind;
+    else if (N <= 32768 && StoreS16::slice_bytes(N) + 1024 <= budget) kind = STORE_S16;
+    else if (N <= 65536 && StoreS16B::slice_bytes(N) + 1024 <= budget) kind = STORE_S16B;
+    else kind = STORE_G32;
+    p.kind = kind;
+
+    size_t store_bytes = kind == STORE_S16 ? StoreS16::slice_bytes(N)
+                       : kind == STORE_S16B ? StoreS16B::slice_bytes(N) : 0;
+    // claim table: exact (one slot per node) when small, else hashed
+    int clog = ilog2_ceil((uint32_t)(N < 64 ? 64 : N));
+    const int clog_max = kind == STORE_G32 ? 12 : 13;
+    if (clog > clog_max) clog = clog_max;
+    while (clog > 8 && store_bytes + ((size_t)4 << clog) > budget) --clog;
+    p.claim_log2 = clog;
+    p.slice_bytes = align16h(store_bytes + ((size_t)4 << clog));
+
+    // warps (runs in flight) per CTA and CTAs per SM: as many runs as shared
+    // memory (228 KB per SM, 1 KB reserved per CTA) and 64 warps allow
+    const size_t sm_total = 228 * 1024;
+    int wpc = 1;
+    if (kind == STORE_G32) {
+        wpc = 8;
+    } else {
+        size_t fit = budget / p.slice_bytes;            // warps that fit one CTA
+        if (fit < 1) fit = 1;
+        wpc = (int)(fit > 8 ? 8 : fit);
+    }
+    // never more warps than runs need
+    long long want = ((long long)R + sms - 1) / sms;
+    if (want < 1) want = 1;
+    if (wpc > want) wpc = (int)want;
+    p.warps_per_cta = wpc;
+    p.smem_bytes = p.slice_bytes * (size_t)wpc;
+    int ctas_per_sm = (int)(sm_total / (p.smem_bytes + 1024));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    int by_warps = 64 / wpc;
+    if (ctas_per_sm > by_warps) ctas_per_sm = by_warps;
+    if (kind == STORE_G32 && ctas_per_sm > 2) ctas_per_sm = 2;
+    long long grid = (long long)sms * ctas_per_sm;
+    long long need = ((long long)R + wpc - 1) / wpc;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    p.grid = (int)grid;
+    p.gscratch_bytes = kind == STORE_G32 ? (size_t)p.grid * wpc * (size_t)N * 4 : 0;
+    return p;
+}
+
+template <class Store>
+static cudaError_t launch_t(const SweepPlan &p, const SweepArgs &a, cudaStream_t s)
+{
+    cudaError_t e = cudaFuncSetAttribute(sweep_kernel<Store>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)p.smem_bytes);
+    if (e != cudaSuccess) return e;
+    sweep_kernel<Store><<<p.grid, p.warps_per_cta * 32, p.smem_bytes, s>>>(a, (uint32_t)p.slice_bytes);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sweep(const SweepPlan &p, const SweepArgs &a, cudaStream_t s)
+{
+    switch (p.kind) {
+    case STORE_S16: return launch_t<StoreS16>(p, a, s);
+    case STORE_S16B: return launch_t<StoreS16B>(p, a, s);
+    default: return launch_t<StoreG32>(p, a, s);
+    }
+}
+
+}  // namespace pz
