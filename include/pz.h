@@ -43,7 +43,7 @@ enum pz_perm_mode {
 };
 
 /* number of 64-bit words per bond count n in the micro accumulators */
-#define PZ_ACC_WORDS 20
+#define PZ_ACC_WORDS 25
 /* columns of a per-run canonical statistics row: P_span, max, moments[5] */
 #define PZ_CANON_COLS 7
 
@@ -87,6 +87,14 @@ int pz_run_rows(pz_ctx *ctx, int32_t R, int perm_mode, const void *perm_src,
                 void *rows_out, int32_t *perms_out);
 
 /*
+ * Bond orders only: the device replacement of RandomState(seed).permutation(M)
+ * (percolate/hpc.py:195,206).  perm_mode is PZ_PERM_MT19937 or PZ_PERM_PHILOX;
+ * seeds host uint32[R]; out int32[R][M] (host, or device when is_device != 0).
+ */
+int pz_make_perms(pz_ctx *ctx, int32_t R, int perm_mode, const uint32_t *seeds,
+                  int32_t *out, int is_device);
+
+/*
  * Fused path: R runs are swept and folded, on the device, into
  *  (a) exact per-n integer sums over runs (micro accumulators) -- the inputs of
  *      _microcanonical_average_* (percolate/percolate.py:450-705), and/or
@@ -105,25 +113,24 @@ int pz_run_fused(pz_ctx *ctx, int32_t R, int perm_mode, const void *perm_src,
 int pz_reset_accumulators(pz_ctx *ctx);
 
 /*
- * Micro accumulators: for n = 0..M, PZ_ACC_WORDS uint64 words
- *   [0] runs with a spanning cluster        [1] sum max      [2] sum max^2
- *   [3] sum c   [4] sum c^2   (c = merges so far; moments[0] = N-1-c)
- *   [5+5j .. 9+5j], j = 0,1,2 for moments[2+j] = m:
- *       sum m as two 64-bit limbs (lo, hi), sum m^2 as three limbs (lo, mid, hi)
- * (moments[1] = N - max needs no words of its own).
- * pz_micro_runs: number of runs folded so far.
- * The export/import pair moves the block to/from caller memory (host, or
- * device when is_device != 0) so that ranks can all-reduce it (plain integer
- * sum per word is NOT valid across limbs: use pz_micro_export_limbs32).
+ * Micro accumulators: for n = 0..M, PZ_ACC_WORDS uint64 words.  Every sum is
+ * held as 32-bit limbs in 64-bit words, so a WORD-WISE integer sum of the
+ * blocks of several contexts (the cross-GPU all-reduce) is exact:
+ *   [0]      runs whose spanning cluster FIRST appears at n (delta form;
+ *            the count of spanning runs at n is the prefix sum)
+ *   [1]      sum max            [2],[3]  sum max^2      (lo32, hi32)
+ *   [4]      sum c              [5],[6]  sum c^2        (c = merges so far;
+ *                                                        moments[0] = N-1-c)
+ *   [7+6j ..12+6j], j = 0,1,2 for moments[2+j] = m:
+ *            sum m (lo32, hi32), sum m^2 (four 32-bit limbs)
+ * (moments[1] = N - max needs no words of its own.)
+ * pz_micro_runs: number of runs folded so far.  Export copies the block to
+ * caller memory (host, or device when is_device != 0); import replaces the
+ * block and the run count (after an all-reduce).
  */
 int64_t pz_micro_runs(const pz_ctx *ctx);
 int pz_micro_export(pz_ctx *ctx, uint64_t *dst, int is_device);
-/* the same sums re-expressed so that a word-wise integer all-reduce (sum) over
- * ranks is exact: every limb is split into 32-bit halves held in 64-bit words.
- * Layout: (M+1) * PZ_ACC_LIMB32_WORDS words. */
-#define PZ_ACC_LIMB32_WORDS 35
-int pz_micro_export_limbs32(pz_ctx *ctx, uint64_t *dst, int is_device);
-int pz_micro_import_limbs32(pz_ctx *ctx, const uint64_t *src, int is_device, int64_t runs);
+int pz_micro_import(pz_ctx *ctx, const uint64_t *src, int is_device, int64_t runs);
 
 /*
  * Per-n means and sample variances from the exact sums (float64), i.e. the
@@ -138,10 +145,11 @@ int pz_micro_finalize(pz_ctx *ctx, double *mean_out, double *var_out);
 /*
  * Binomial weights: replaces _binomial_pmf (percolate/percolate.py:1067-1109),
  * one p per thread, the reference's mode-outward ratio recurrence in the
- * reference's operation order.  pmf_out: host double[num_p][M+1] (may be NULL
- * to keep the table on the device only, for pz_convolve / PZ_FUSE_CANON).
+ * reference's operation order, for M bonds (no graph needed).  pmf_out: host
+ * double[num_p][M+1] (may be NULL to keep the table on the device only, for
+ * pz_convolve / PZ_FUSE_CANON; the latter needs M = bonds of the graph).
  */
-int pz_set_ps(pz_ctx *ctx, int32_t num_p, const double *ps, double *pmf_out);
+int pz_set_ps(pz_ctx *ctx, int32_t M, int32_t num_p, const double *ps, double *pmf_out);
 
 /*
  * out[c][p] = sum_n pmf_p[n] * cols[c][n]: the contraction of canonical_averages
@@ -153,12 +161,12 @@ int pz_convolve(pz_ctx *ctx, int32_t num_cols, const double *cols, double *out);
 
 /*
  * bond_canonical_statistics for one materialised run (percolate/hpc.py:443-515):
- *   rows  host packed rows of ONE run ((M+1) * pz_row_bytes());
+ *   rows  host packed rows of ONE run, (M+1) * (spanning ? 53 : 52) bytes (no graph needed);
  *   f     host double[M+1] convolution factors;  out  host double[PZ_CANON_COLS]
  *         (out[0] = percolation probability, 0 when spanning is off)
  */
-int pz_canonical_statistics_rows(pz_ctx *ctx, const void *rows, const double *f,
-                                 double *out);
+int pz_canonical_statistics_rows(pz_ctx *ctx, int32_t M, int spanning, const void *rows,
+                                 const double *f, double *out);
 
 /*
  * Canonical accumulators of the fused path (PZ_FUSE_CANON), the state of
@@ -169,10 +177,28 @@ int pz_canonical_statistics_rows(pz_ctx *ctx, const void *rows, const double *f,
  */
 int pz_canon_export(pz_ctx *ctx, int64_t *count_out, double *mean_out, double *m2_out);
 int pz_canon_merge(pz_ctx *ctx, int64_t count, const double *mean, const double *m2);
+/* forget the canonical partials only (the micro accumulators are kept) */
+int pz_canon_reset(pz_ctx *ctx);
 
 /* per-run canonical statistics of the LAST pz_run_fused(PZ_FUSE_CANON) call:
  * host double[R][num_p][PZ_CANON_COLS] (parity tests, small R) */
 int pz_canon_last_runs(pz_ctx *ctx, double *out);
+
+/*
+ * Per-phase device time, measured with CUDA events on the context's stream
+ * around the launches of each kernel family (off by default; enabling resets
+ * the counters).  ms_out / launches_out have PZ_PHASES entries.
+ */
+#define PZ_PHASES 7
+#define PZ_PHASE_PERM 0     /* bond orders (Philox / MT19937)       */
+#define PZ_PHASE_SWEEP 1    /* union-find sweep                      */
+#define PZ_PHASE_ACCUM 2    /* per-n exact sums over runs            */
+#define PZ_PHASE_CANON 3    /* per-run binomial contraction          */
+#define PZ_PHASE_REDUCE 4   /* (mean, M2) over the runs of a batch   */
+#define PZ_PHASE_ROWS 5     /* row materialisation                   */
+#define PZ_PHASE_CKPT 6     /* run-state checkpoints (block scan)    */
+int pz_profile(pz_ctx *ctx, int enable);
+int pz_profile_read(pz_ctx *ctx, double *ms_out, int64_t *launches_out);
 
 /* number of kernels this context has launched since creation */
 int64_t pz_launch_count(const pz_ctx *ctx);

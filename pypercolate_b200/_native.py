@@ -30,7 +30,7 @@ SYMBOLS = [
     "pz_micro_export", "pz_micro_import", "pz_micro_finalize", "pz_set_ps",
     "pz_convolve", "pz_canonical_statistics_rows", "pz_canon_export",
     "pz_canon_merge", "pz_canon_last_runs", "pz_launch_count",
-    "pz_make_perms",
+    "pz_make_perms", "pz_profile", "pz_profile_read", "pz_canon_reset",
 ]
 
 
@@ -79,12 +79,15 @@ def load():
         L.pz_micro_export.argtypes = [vp, vp, ci]
         L.pz_micro_import.argtypes = [vp, vp, ci, i64]
         L.pz_micro_finalize.argtypes = [vp, vp, vp]
-        L.pz_set_ps.argtypes = [vp, i32, vp, vp]
+        L.pz_set_ps.argtypes = [vp, i32, i32, vp, vp]
         L.pz_convolve.argtypes = [vp, i32, vp, vp]
-        L.pz_canonical_statistics_rows.argtypes = [vp, vp, vp, vp]
+        L.pz_canonical_statistics_rows.argtypes = [vp, i32, ci, vp, vp, vp]
+        L.pz_profile.argtypes = [vp, ci]
+        L.pz_profile_read.argtypes = [vp, vp, vp]
         L.pz_canon_export.argtypes = [vp, ctypes.POINTER(i64), vp, vp]
         L.pz_canon_merge.argtypes = [vp, i64, vp, vp]
         L.pz_canon_last_runs.argtypes = [vp, vp]
+        L.pz_canon_reset.argtypes = [vp]
         L.pz_launch_count.argtypes = [vp]
         L.pz_launch_count.restype = i64
         _lib = L
@@ -114,6 +117,7 @@ class Context(object):
         self.N = self.M = 0
         self.spanning = False
         self.num_p = 0
+        self.pmf_M = -1
 
     def close(self):
         if getattr(self, "_h", None):
@@ -220,27 +224,45 @@ class Context(object):
         return mean, var
 
     # -- canonical ------------------------------------------------------------
-    def set_ps(self, ps, want_pmf=False):
+    def set_ps(self, ps, want_pmf=False, M=None):
         ps = np.ascontiguousarray(ps, dtype=np.float64).reshape(-1)
-        pmf = np.empty((ps.size, self.M + 1), dtype=np.float64) if want_pmf else None
-        _check(self._L.pz_set_ps(self._h, ps.size, _ptr(ps), _ptr(pmf)))
+        M = self.M if M is None else int(M)
+        pmf = np.empty((ps.size, M + 1), dtype=np.float64) if want_pmf else None
+        _check(self._L.pz_set_ps(self._h, M, ps.size, _ptr(ps), _ptr(pmf)))
         self.num_p = ps.size
+        self.pmf_M = M
         return pmf
 
     def convolve(self, cols):
         cols = np.ascontiguousarray(cols, dtype=np.float64)
-        if cols.ndim != 2 or cols.shape[1] != self.M + 1:
+        if cols.ndim != 2 or cols.shape[1] != self.pmf_M + 1:
             raise ValueError("cols must have shape (num_cols, num_edges + 1)")
         out = np.empty((cols.shape[0], self.num_p), dtype=np.float64)
         _check(self._L.pz_convolve(self._h, cols.shape[0], _ptr(cols), _ptr(out)))
         return out
 
-    def canonical_statistics_rows(self, rows, f):
+    def canonical_statistics_rows(self, rows, f, spanning=None):
         rows = np.ascontiguousarray(rows)
         f = np.ascontiguousarray(f, dtype=np.float64)
+        if spanning is None:
+            spanning = 'has_spanning_cluster' in rows.dtype.names
+        if rows.dtype.itemsize != (53 if spanning else 52) or f.size != rows.size:
+            raise ValueError("rows must be packed microcanonical statistics of one run")
         out = np.empty(CANON_COLS, dtype=np.float64)
-        _check(self._L.pz_canonical_statistics_rows(self._h, _ptr(rows), _ptr(f), _ptr(out)))
+        _check(self._L.pz_canonical_statistics_rows(self._h, rows.size - 1, int(bool(spanning)),
+                                                    _ptr(rows), _ptr(f), _ptr(out)))
         return out
+
+    PHASES = ("perm", "sweep", "accumulate", "canon_runs", "canon_reduce", "rows", "checkpoints")
+
+    def profile(self, enable=True):
+        _check(self._L.pz_profile(self._h, int(bool(enable))))
+
+    def profile_read(self):
+        ms = np.zeros(len(self.PHASES), dtype=np.float64)
+        cnt = np.zeros(len(self.PHASES), dtype=np.int64)
+        _check(self._L.pz_profile_read(self._h, _ptr(ms), _ptr(cnt)))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PHASES)}
 
     def canon_export(self):
         cnt = ctypes.c_int64()
@@ -253,6 +275,11 @@ class Context(object):
         mean = np.ascontiguousarray(mean, dtype=np.float64)
         m2 = np.ascontiguousarray(m2, dtype=np.float64)
         _check(self._L.pz_canon_merge(self._h, int(count), _ptr(mean), _ptr(m2)))
+
+    def canon_replace(self, count, mean, m2):
+        _check(self._L.pz_canon_reset(self._h))
+        if count:
+            self.canon_merge(count, mean, m2)
 
     def canon_last_runs(self, R):
         out = np.empty((R, self.num_p, CANON_COLS), dtype=np.float64)

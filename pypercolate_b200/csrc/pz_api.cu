@@ -50,7 +50,7 @@ struct pz_ctx {
     int sms = 0;
     size_t smem_optin = 0;
     int force_kind = -1;
-    size_t chunk_bytes = (size_t)4 << 30;
+    size_t chunk_bytes = (size_t)8 << 30;
 
     // graph
     int32_t N = 0, M = 0;
@@ -70,37 +70,87 @@ struct pz_ctx {
 
     // micro accumulators
     DevBuf<unsigned long long> acc;       // (M+1) * PZ_ACC_WORDS
-    DevBuf<unsigned long long> span_hist; // M + 2
+    DevBuf<unsigned long long> span_cum;  // M + 1
+    DevBuf<double> fin;                   // 13 * (M+1): mean[7], var[6]
     int64_t micro_runs = 0;
+    DevBuf<RunState> ckpt;                // [R][n_ckpt] run state every ckpt_every rows
+    int ckpt_every = 1024;
 
     // canonical
     int32_t num_p = 0;
+    int32_t pmf_M = -1;                   // number of bonds the weights were built for
     std::vector<double> ps;
-    DevBuf<double> pmf;                   // [num_p][M+1]
-    std::vector<int32_t> band_lo, band_hi;
-    DevBuf<double> dense;                 // scratch of the contraction
+    std::vector<int32_t> porder;          // sorted position -> caller's index
+    DevBuf<double> ps_dev;
+    DevBuf<double> pmf;                   // [num_p][M+1], rows in ascending-p order
+    DevBuf<int32_t> band_lo, band_hi, porder_dev;
+    DevBuf<double> cols;                  // scratch of the contraction
+    DevBuf<double> cols_out;
+    DevBuf<double> canon_red;             // 2 * num_p * 7
     DevBuf<double> canon_runs;            // [R][num_p][7] of the last fused call
     int32_t canon_last_R = 0;
     int64_t canon_count = 0;
     std::vector<double> canon_mean, canon_m2;
 
     int64_t launches = 0;
+
+    // optional per-phase device timing (CUDA events on this context's stream)
+    bool profiling = false;
+    double phase_ms[PZ_PHASES] = {0};
+    int64_t phase_launches[PZ_PHASES] = {0};
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
 };
+
+struct PhaseTimer {
+    pz_ctx *c; int phase; cudaEvent_t a = nullptr, b = nullptr;
+    PhaseTimer(pz_ctx *c_, int phase_) : c(c_), phase(phase_) {
+        if (!c->profiling) return;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, c->stream);
+    }
+    ~PhaseTimer() {
+        if (!c->profiling) return;
+        cudaEventRecord(b, c->stream);
+        c->pending.push_back({phase, {a, b}});
+    }
+};
+
+static void collect_phases(pz_ctx *c)
+{
+    for (auto &p : c->pending) {
+        cudaEventSynchronize(p.second.second);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, p.second.first, p.second.second);
+        c->phase_ms[p.first] += ms;
+        c->phase_launches[p.first] += 1;
+        cudaEventDestroy(p.second.first);
+        cudaEventDestroy(p.second.second);
+    }
+    c->pending.clear();
+}
 
 // implemented in the other translation units
 namespace pz {
-cudaError_t launch_accumulate(const StatsArgs &a, unsigned long long *acc,
-                              unsigned long long *span_hist, cudaStream_t s, int *launches);
+cudaError_t launch_checkpoints(const StatsArgs &a, RunState *ckpt, int every, int n_ckpt,
+                               cudaStream_t s);
+cudaError_t launch_accumulate(const StatsArgs &a, unsigned long long *acc, const RunState *ckpt,
+                              int seg, int n_ckpt, cudaStream_t s);
 cudaError_t launch_micro_finalize(int32_t N, int32_t M, int64_t runs, const unsigned long long *acc,
-                                  const unsigned long long *span_hist, double *mean, double *var,
+                                  unsigned long long *span_cum, double *mean, double *var,
                                   cudaStream_t s);
-cudaError_t launch_binomial_pmf(int32_t M, int32_t num_p, const double *ps_dev, double *pmf,
-                                cudaStream_t s);
-cudaError_t launch_convolve(int32_t M, int32_t num_p, const double *pmf, int32_t num_cols,
-                            const double *cols, double *out, cudaStream_t s);
-cudaError_t launch_canon_runs(const StatsArgs &a, int32_t num_p, const double *pmf,
-                              const int32_t *band_lo, const int32_t *band_hi, double *out,
-                              cudaStream_t s, int *launches);
+cudaError_t launch_binomial_pmf(int32_t M, int32_t P, const double *ps_dev, double *pmf,
+                                int32_t *band_lo, int32_t *band_hi, cudaStream_t s);
+cudaError_t launch_convolve(int32_t M, int32_t P, const double *pmf, const int32_t *band_lo,
+                            const int32_t *band_hi, int32_t num_cols, const double *cols,
+                            double *out, cudaStream_t s);
+cudaError_t launch_canon_rows(int32_t M, int spanning, const uint8_t *rows, const double *f,
+                              double *out, cudaStream_t s);
+cudaError_t launch_canon_runs(const StatsArgs &a, int32_t P, const double *pmf,
+                              const int32_t *band_lo, const int32_t *band_hi, const int32_t *porder,
+                              const RunState *ckpt, int ckpt_every, int n_ckpt, double *out,
+                              cudaStream_t s);
+cudaError_t launch_canon_reduce(int32_t R, int32_t cols, const double *runs, double *mean,
+                                double *m2, cudaStream_t s);
 cudaError_t launch_perm_philox(int32_t M, int32_t R, const uint32_t *seeds, int32_t *perms,
                                cudaStream_t s, int *launches);
 cudaError_t launch_perm_mt19937(int32_t M, int32_t R, const uint32_t *seeds, int32_t *perms,
@@ -140,8 +190,10 @@ void pz_destroy(pz_ctx *c)
     cudaStreamSynchronize(c->stream);
     c->edges32.release(); c->edges64.release(); c->sides2.release();
     c->perms.release(); c->recs.release(); c->nspan.release(); c->gscratch.release();
-    c->rows.release(); c->seeds.release(); c->acc.release(); c->span_hist.release();
-    c->pmf.release(); c->dense.release(); c->canon_runs.release();
+    c->rows.release(); c->seeds.release(); c->acc.release(); c->span_cum.release();
+    c->fin.release(); c->ckpt.release(); c->ps_dev.release(); c->band_lo.release();
+    c->band_hi.release(); c->porder_dev.release(); c->cols.release(); c->cols_out.release();
+    c->canon_red.release(); c->pmf.release(); c->canon_runs.release();
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -204,8 +256,7 @@ int pz_set_graph(pz_ctx *c, int32_t N, int32_t M, const int32_t *eu, const int32
     PZ_CUDA(cudaStreamSynchronize(c->stream));
     // graph change invalidates everything derived from it
     c->micro_runs = 0;
-    c->acc.release(); c->span_hist.release();
-    c->num_p = 0; c->pmf.release();
+    c->acc.release(); c->span_cum.release();
     c->canon_count = 0; c->canon_last_R = 0;
     return PZ_OK;
 }
@@ -243,6 +294,7 @@ static int sweep_chunk(pz_ctx *c, int32_t R, int perm_mode, const void *perm_src
             PZ_CUDA(cudaMemcpyAsync(c->seeds.p, (const uint32_t *)perm_src + run0, (size_t)R * 4,
                                     cudaMemcpyHostToDevice, c->stream));
             int l = 0;
+            PhaseTimer t(c, PZ_PHASE_PERM);
             if (perm_mode == PZ_PERM_PHILOX)
                 PZ_CUDA(launch_perm_philox(M, R, c->seeds.p, c->perms.p, c->stream, &l));
             else
@@ -268,7 +320,10 @@ static int sweep_chunk(pz_ctx *c, int32_t R, int perm_mode, const void *perm_src
     sa.nspan = c->nspan.p;
     sa.gscratch = c->gscratch.p;
     sa.claim_log2 = plan.claim_log2;
-    PZ_CUDA(launch_sweep(plan, sa, c->stream));
+    {
+        PhaseTimer t(c, PZ_PHASE_SWEEP);
+        PZ_CUDA(launch_sweep(plan, sa, c->stream));
+    }
     c->launches += 1;
 
     out->plan = plan;
@@ -307,7 +362,10 @@ int pz_run_rows(pz_ctx *c, int32_t R, int perm_mode, const void *perm_src, void 
         rc = sweep_chunk(c, rc_n, perm_mode, perm_src, r0, &ch);
         if (rc) return rc;
         PZ_CUDA(c->rows.ensure((size_t)rc_n * run_bytes));
-        PZ_CUDA(launch_expand_rows(ch.stats, c->rows.p, c->stream));
+        {
+            PhaseTimer t(c, PZ_PHASE_ROWS);
+            PZ_CUDA(launch_expand_rows(ch.stats, c->rows.p, c->stream));
+        }
         c->launches += 1;
         PZ_CUDA(cudaMemcpyAsync((uint8_t *)rows_out + r0 * run_bytes, c->rows.p,
                                 (size_t)rc_n * run_bytes, cudaMemcpyDeviceToHost, c->stream));
@@ -321,20 +379,333 @@ int pz_run_rows(pz_ctx *c, int32_t R, int perm_mode, const void *perm_src, void 
 
 }  // extern "C"
 
-// ---- TEMPORARY stubs (replaced as the kernels land) -------------------------
-extern "C" {
-#define PZ_STUB(name, ...) int name(__VA_ARGS__) { return fail(PZ_ERR_STATE, #name ": not implemented yet"); }
-PZ_STUB(pz_make_perms, pz_ctx *, int32_t, int, const uint32_t *, int32_t *, int)
-PZ_STUB(pz_run_fused, pz_ctx *, int32_t, int, const void *, int)
-PZ_STUB(pz_reset_accumulators, pz_ctx *)
-int64_t pz_micro_runs(const pz_ctx *c) { return c ? c->micro_runs : 0; }
-PZ_STUB(pz_micro_export, pz_ctx *, uint64_t *, int)
-PZ_STUB(pz_micro_import, pz_ctx *, const uint64_t *, int, int64_t)
-PZ_STUB(pz_micro_finalize, pz_ctx *, double *, double *)
-PZ_STUB(pz_set_ps, pz_ctx *, int32_t, const double *, double *)
-PZ_STUB(pz_convolve, pz_ctx *, int32_t, const double *, double *)
-PZ_STUB(pz_canonical_statistics_rows, pz_ctx *, const void *, const double *, double *)
-PZ_STUB(pz_canon_export, pz_ctx *, int64_t *, double *, double *)
-PZ_STUB(pz_canon_merge, pz_ctx *, int64_t, const double *, const double *)
-PZ_STUB(pz_canon_last_runs, pz_ctx *, double *)
+
+// ---------------------------------------------------------------------------
+// fused path
+// ---------------------------------------------------------------------------
+static int ensure_acc(pz_ctx *c)
+{
+    const size_t words = ((size_t)c->M + 1) * PZ_ACC_WORDS;
+    if (c->acc.cap < words) {
+        PZ_CUDA(c->acc.ensure(words));
+        PZ_CUDA(cudaMemsetAsync(c->acc.p, 0, words * 8, c->stream));
+        c->micro_runs = 0;
+    }
+    return PZ_OK;
 }
+
+static void chan_merge(int64_t &na, std::vector<double> &mean_a, std::vector<double> &m2_a,
+                       int64_t nb, const double *mean_b, const double *m2_b)
+{
+    // Chan et al. pairwise merge -- the arithmetic bond_reduce delegates to
+    // simoa.stats.online_variance (percolate/hpc.py:677-684)
+    if (nb <= 0) return;
+    if (na == 0) {
+        mean_a.assign(mean_b, mean_b + mean_a.size());
+        m2_a.assign(m2_b, m2_b + m2_a.size());
+        na = nb;
+        return;
+    }
+    const double fa = (double)na, fb = (double)nb, n = fa + fb;
+    for (size_t i = 0; i < mean_a.size(); ++i) {
+        const double delta = mean_b[i] - mean_a[i];
+        mean_a[i] = mean_a[i] + delta * fb / n;
+        m2_a[i] = m2_a[i] + m2_b[i] + delta * delta * fa * fb / n;
+    }
+    na += nb;
+}
+
+extern "C" {
+
+int pz_make_perms(pz_ctx *c, int32_t R, int perm_mode, const uint32_t *seeds, int32_t *out,
+                  int is_device)
+{
+    if (!c) return fail(PZ_ERR_ARG, "null context");
+    if (c->N == 0) return fail(PZ_ERR_STATE, "no graph set (call pz_set_graph first)");
+    if (perm_mode != PZ_PERM_MT19937 && perm_mode != PZ_PERM_PHILOX)
+        return fail(PZ_ERR_ARG, "pz_make_perms: perm_mode must be a device RNG mode");
+    if (R < 0 || (R > 0 && (!seeds || !out))) return fail(PZ_ERR_ARG, "pz_make_perms: bad arguments");
+    if (R == 0 || c->M == 0) return PZ_OK;
+    PZ_CUDA(cudaSetDevice(c->device));
+    const size_t per_run = (size_t)c->M * 4;
+    const size_t chunk = is_device ? (size_t)R : std::max<size_t>(1, c->chunk_bytes / per_run);
+    for (size_t r0 = 0; r0 < (size_t)R; r0 += chunk) {
+        const int32_t n = (int32_t)std::min(chunk, (size_t)R - r0);
+        PZ_CUDA(c->seeds.ensure((size_t)n));
+        PZ_CUDA(cudaMemcpyAsync(c->seeds.p, seeds + r0, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+        int32_t *dst = out + r0 * (size_t)c->M;
+        if (!is_device) { PZ_CUDA(c->perms.ensure((size_t)n * c->M)); dst = c->perms.p; }
+        int l = 0;
+        {
+            PhaseTimer t(c, PZ_PHASE_PERM);
+            if (perm_mode == PZ_PERM_PHILOX) PZ_CUDA(launch_perm_philox(c->M, n, c->seeds.p, dst, c->stream, &l));
+            else PZ_CUDA(launch_perm_mt19937(c->M, n, c->seeds.p, dst, c->stream, &l));
+        }
+        c->launches += l;
+        if (!is_device)
+            PZ_CUDA(cudaMemcpyAsync(out + r0 * (size_t)c->M, dst, (size_t)n * per_run,
+                                    cudaMemcpyDeviceToHost, c->stream));
+        PZ_CUDA(cudaStreamSynchronize(c->stream));
+        if (c->profiling) collect_phases(c);
+    }
+    return PZ_OK;
+}
+
+int pz_reset_accumulators(pz_ctx *c)
+{
+    if (!c) return fail(PZ_ERR_ARG, "null context");
+    PZ_CUDA(cudaSetDevice(c->device));
+    if (c->acc.p)
+        PZ_CUDA(cudaMemsetAsync(c->acc.p, 0, ((size_t)c->M + 1) * PZ_ACC_WORDS * 8, c->stream));
+    c->micro_runs = 0;
+    c->canon_count = 0;
+    c->canon_last_R = 0;
+    return PZ_OK;
+}
+
+int pz_run_fused(pz_ctx *c, int32_t R, int perm_mode, const void *perm_src, int flags)
+{
+    int rc = check_run_args(c, R, perm_mode, perm_src);
+    if (rc) return rc;
+    if (!(flags & (PZ_FUSE_MICRO | PZ_FUSE_CANON))) return fail(PZ_ERR_ARG, "pz_run_fused: no flags");
+    if ((flags & PZ_FUSE_CANON) && (c->num_p == 0 || c->pmf_M != c->M))
+        return fail(PZ_ERR_STATE, "pz_run_fused: PZ_FUSE_CANON needs pz_set_ps(M = bonds of the graph) first");
+    PZ_CUDA(cudaSetDevice(c->device));
+    if (flags & PZ_FUSE_MICRO) { rc = ensure_acc(c); if (rc) return rc; }
+    const int P = c->num_p;
+    const size_t per_run = (size_t)std::max(c->M, 1) * 12;       // perms + widest records
+    const size_t chunk = std::max<size_t>(1, c->chunk_bytes / per_run);
+    const int n_ckpt = c->M / c->ckpt_every + 1;
+    for (size_t r0 = 0; r0 < (size_t)R; r0 += chunk) {
+        const int32_t n = (int32_t)std::min(chunk, (size_t)R - r0);
+        Chunk ch;
+        rc = sweep_chunk(c, n, perm_mode, perm_src, r0, &ch);
+        if (rc) return rc;
+        PZ_CUDA(c->ckpt.ensure((size_t)n * n_ckpt));
+        RunState *ck = c->ckpt.p;
+        {
+            PhaseTimer t(c, PZ_PHASE_CKPT);
+            PZ_CUDA(launch_checkpoints(ch.stats, ck, c->ckpt_every, n_ckpt, c->stream));
+        }
+        c->launches += 1;
+        if (flags & PZ_FUSE_MICRO) {
+            PhaseTimer t(c, PZ_PHASE_ACCUM);
+            PZ_CUDA(launch_accumulate(ch.stats, c->acc.p, ck, c->ckpt_every, n_ckpt, c->stream));
+            c->launches += 1;
+            c->micro_runs += n;
+        }
+        if (flags & PZ_FUSE_CANON) {
+            const int cols = P * PZ_CANON_COLS;
+            PZ_CUDA(c->canon_runs.ensure((size_t)n * cols));
+            PZ_CUDA(c->canon_red.ensure((size_t)2 * cols));
+            {
+                PhaseTimer t(c, PZ_PHASE_CANON);
+                PZ_CUDA(launch_canon_runs(ch.stats, P, c->pmf.p, c->band_lo.p, c->band_hi.p,
+                                          c->porder_dev.p, ck, c->ckpt_every, n_ckpt,
+                                          c->canon_runs.p, c->stream));
+            }
+            {
+                PhaseTimer t(c, PZ_PHASE_REDUCE);
+                PZ_CUDA(launch_canon_reduce(n, cols, c->canon_runs.p, c->canon_red.p,
+                                            c->canon_red.p + cols, c->stream));
+            }
+            c->launches += 2;
+            std::vector<double> red((size_t)2 * cols);
+            PZ_CUDA(cudaMemcpyAsync(red.data(), c->canon_red.p, red.size() * 8,
+                                    cudaMemcpyDeviceToHost, c->stream));
+            PZ_CUDA(cudaStreamSynchronize(c->stream));
+            c->canon_mean.resize(cols); c->canon_m2.resize(cols);
+            chan_merge(c->canon_count, c->canon_mean, c->canon_m2, n, red.data(), red.data() + cols);
+            c->canon_last_R = n;
+        }
+        if (c->profiling) collect_phases(c);
+    }
+    return PZ_OK;
+}
+
+int64_t pz_micro_runs(const pz_ctx *c) { return c ? c->micro_runs : 0; }
+
+int pz_micro_export(pz_ctx *c, uint64_t *dst, int is_device)
+{
+    if (!c || !dst) return fail(PZ_ERR_ARG, "pz_micro_export: bad arguments");
+    if (c->N == 0) return fail(PZ_ERR_STATE, "no graph set");
+    PZ_CUDA(cudaSetDevice(c->device));
+    int rc = ensure_acc(c); if (rc) return rc;
+    PZ_CUDA(cudaMemcpyAsync(dst, c->acc.p, ((size_t)c->M + 1) * PZ_ACC_WORDS * 8,
+                            is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+    PZ_CUDA(cudaStreamSynchronize(c->stream));
+    return PZ_OK;
+}
+
+int pz_micro_import(pz_ctx *c, const uint64_t *src, int is_device, int64_t runs)
+{
+    if (!c || !src || runs < 0) return fail(PZ_ERR_ARG, "pz_micro_import: bad arguments");
+    if (c->N == 0) return fail(PZ_ERR_STATE, "no graph set");
+    PZ_CUDA(cudaSetDevice(c->device));
+    int rc = ensure_acc(c); if (rc) return rc;
+    PZ_CUDA(cudaMemcpyAsync(c->acc.p, src, ((size_t)c->M + 1) * PZ_ACC_WORDS * 8,
+                            is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+    PZ_CUDA(cudaStreamSynchronize(c->stream));
+    c->micro_runs = runs;
+    return PZ_OK;
+}
+
+int pz_micro_finalize(pz_ctx *c, double *mean_out, double *var_out)
+{
+    if (!c || !mean_out || !var_out) return fail(PZ_ERR_ARG, "pz_micro_finalize: bad arguments");
+    if (c->N == 0) return fail(PZ_ERR_STATE, "no graph set");
+    if (c->micro_runs <= 0 || !c->acc.p) return fail(PZ_ERR_STATE, "pz_micro_finalize: no runs accumulated");
+    PZ_CUDA(cudaSetDevice(c->device));
+    const size_t S = (size_t)c->M + 1;
+    PZ_CUDA(c->span_cum.ensure(S));
+    PZ_CUDA(c->fin.ensure(13 * S));
+    PZ_CUDA(launch_micro_finalize(c->N, c->M, c->micro_runs, c->acc.p, c->span_cum.p, c->fin.p,
+                                  c->fin.p + 7 * S, c->stream));
+    c->launches += 2;
+    PZ_CUDA(cudaMemcpyAsync(mean_out, c->fin.p, 7 * S * 8, cudaMemcpyDeviceToHost, c->stream));
+    PZ_CUDA(cudaMemcpyAsync(var_out, c->fin.p + 7 * S, 6 * S * 8, cudaMemcpyDeviceToHost, c->stream));
+    PZ_CUDA(cudaStreamSynchronize(c->stream));
+    return PZ_OK;
+}
+
+int pz_set_ps(pz_ctx *c, int32_t M, int32_t num_p, const double *ps, double *pmf_out)
+{
+    if (!c) return fail(PZ_ERR_ARG, "null context");
+    if (M < 0) return fail(PZ_ERR_ARG, "pz_set_ps: M must be >= 0");
+    if (num_p < 0 || (num_p > 0 && !ps)) return fail(PZ_ERR_ARG, "pz_set_ps: bad arguments");
+    for (int i = 0; i < num_p; ++i)
+        if (!(ps[i] >= 0.0 && ps[i] <= 1.0)) return fail(PZ_ERR_ARG, "pz_set_ps: p must lie in [0, 1]");
+    PZ_CUDA(cudaSetDevice(c->device));
+    c->num_p = num_p;
+    c->pmf_M = M;
+    c->ps.assign(ps, ps + num_p);
+    c->canon_count = 0; c->canon_last_R = 0;
+    if (num_p == 0) return PZ_OK;
+    c->porder.resize(num_p);
+    for (int i = 0; i < num_p; ++i) c->porder[i] = i;
+    std::stable_sort(c->porder.begin(), c->porder.end(),
+                     [&](int a, int b) { return ps[a] < ps[b]; });
+    std::vector<double> sorted(num_p);
+    for (int i = 0; i < num_p; ++i) sorted[i] = ps[c->porder[i]];
+    const size_t S = (size_t)M + 1;
+    PZ_CUDA(c->ps_dev.ensure(num_p));
+    PZ_CUDA(c->pmf.ensure((size_t)num_p * S));
+    PZ_CUDA(c->band_lo.ensure(num_p));
+    PZ_CUDA(c->band_hi.ensure(num_p));
+    PZ_CUDA(c->porder_dev.ensure(num_p));
+    PZ_CUDA(cudaMemcpyAsync(c->ps_dev.p, sorted.data(), (size_t)num_p * 8, cudaMemcpyHostToDevice, c->stream));
+    PZ_CUDA(cudaMemcpyAsync(c->porder_dev.p, c->porder.data(), (size_t)num_p * 4, cudaMemcpyHostToDevice, c->stream));
+    PZ_CUDA(launch_binomial_pmf(M, num_p, c->ps_dev.p, c->pmf.p, c->band_lo.p, c->band_hi.p, c->stream));
+    c->launches += 2;
+    if (pmf_out)
+        for (int i = 0; i < num_p; ++i)
+            PZ_CUDA(cudaMemcpyAsync(pmf_out + (size_t)c->porder[i] * S, c->pmf.p + (size_t)i * S, S * 8,
+                                    cudaMemcpyDeviceToHost, c->stream));
+    PZ_CUDA(cudaStreamSynchronize(c->stream));
+    return PZ_OK;
+}
+
+int pz_convolve(pz_ctx *c, int32_t num_cols, const double *cols, double *out)
+{
+    if (!c || num_cols < 0 || (num_cols > 0 && (!cols || !out)))
+        return fail(PZ_ERR_ARG, "pz_convolve: bad arguments");
+    if (c->num_p == 0) return fail(PZ_ERR_STATE, "pz_convolve: call pz_set_ps first");
+    if (num_cols == 0) return PZ_OK;
+    PZ_CUDA(cudaSetDevice(c->device));
+    const size_t S = (size_t)c->pmf_M + 1;
+    const int P = c->num_p;
+    PZ_CUDA(c->cols.ensure((size_t)num_cols * S));
+    PZ_CUDA(c->cols_out.ensure((size_t)num_cols * P));
+    PZ_CUDA(cudaMemcpyAsync(c->cols.p, cols, (size_t)num_cols * S * 8, cudaMemcpyHostToDevice, c->stream));
+    PZ_CUDA(launch_convolve(c->pmf_M, P, c->pmf.p, c->band_lo.p, c->band_hi.p, num_cols, c->cols.p,
+                            c->cols_out.p, c->stream));
+    c->launches += 1;
+    std::vector<double> tmp((size_t)num_cols * P);
+    PZ_CUDA(cudaMemcpyAsync(tmp.data(), c->cols_out.p, tmp.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+    PZ_CUDA(cudaStreamSynchronize(c->stream));
+    for (int col = 0; col < num_cols; ++col)
+        for (int i = 0; i < P; ++i)
+            out[(size_t)col * P + c->porder[i]] = tmp[(size_t)col * P + i];
+    return PZ_OK;
+}
+
+int pz_canonical_statistics_rows(pz_ctx *c, int32_t M, int spanning, const void *rows,
+                                 const double *f, double *out)
+{
+    if (!c || M < 0 || !rows || !f || !out)
+        return fail(PZ_ERR_ARG, "pz_canonical_statistics_rows: bad arguments");
+    PZ_CUDA(cudaSetDevice(c->device));
+    const size_t S = (size_t)M + 1, rb = spanning ? 53 : 52;
+    PZ_CUDA(c->rows.ensure(S * rb));
+    PZ_CUDA(c->cols.ensure(S + 8));
+    PZ_CUDA(cudaMemcpyAsync(c->rows.p, rows, S * rb, cudaMemcpyHostToDevice, c->stream));
+    PZ_CUDA(cudaMemcpyAsync(c->cols.p, f, S * 8, cudaMemcpyHostToDevice, c->stream));
+    PZ_CUDA(launch_canon_rows(M, spanning ? 1 : 0, c->rows.p, c->cols.p, c->cols.p + S, c->stream));
+    c->launches += 1;
+    PZ_CUDA(cudaMemcpyAsync(out, c->cols.p + S, 7 * 8, cudaMemcpyDeviceToHost, c->stream));
+    PZ_CUDA(cudaStreamSynchronize(c->stream));
+    return PZ_OK;
+}
+
+int pz_canon_export(pz_ctx *c, int64_t *count_out, double *mean_out, double *m2_out)
+{
+    if (!c || !count_out || !mean_out || !m2_out) return fail(PZ_ERR_ARG, "pz_canon_export: bad arguments");
+    if (c->num_p == 0) return fail(PZ_ERR_STATE, "pz_canon_export: call pz_set_ps first");
+    const size_t cols = (size_t)c->num_p * PZ_CANON_COLS;
+    *count_out = c->canon_count;
+    for (size_t i = 0; i < cols; ++i) {
+        mean_out[i] = c->canon_count ? c->canon_mean[i] : 0.0;
+        m2_out[i] = c->canon_count ? c->canon_m2[i] : 0.0;
+    }
+    return PZ_OK;
+}
+
+int pz_canon_merge(pz_ctx *c, int64_t count, const double *mean, const double *m2)
+{
+    if (!c || count < 0 || !mean || !m2) return fail(PZ_ERR_ARG, "pz_canon_merge: bad arguments");
+    if (c->num_p == 0) return fail(PZ_ERR_STATE, "pz_canon_merge: call pz_set_ps first");
+    const size_t cols = (size_t)c->num_p * PZ_CANON_COLS;
+    c->canon_mean.resize(cols); c->canon_m2.resize(cols);
+    chan_merge(c->canon_count, c->canon_mean, c->canon_m2, count, mean, m2);
+    return PZ_OK;
+}
+
+int pz_canon_reset(pz_ctx *c)
+{
+    if (!c) return fail(PZ_ERR_ARG, "null context");
+    c->canon_count = 0;
+    return PZ_OK;
+}
+
+int pz_canon_last_runs(pz_ctx *c, double *out)
+{
+    if (!c || !out) return fail(PZ_ERR_ARG, "pz_canon_last_runs: bad arguments");
+    if (c->canon_last_R == 0) return fail(PZ_ERR_STATE, "pz_canon_last_runs: no fused canonical batch yet");
+    PZ_CUDA(cudaSetDevice(c->device));
+    PZ_CUDA(cudaMemcpyAsync(out, c->canon_runs.p,
+                            (size_t)c->canon_last_R * c->num_p * PZ_CANON_COLS * 8,
+                            cudaMemcpyDeviceToHost, c->stream));
+    PZ_CUDA(cudaStreamSynchronize(c->stream));
+    return PZ_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+int pz_profile(pz_ctx *c, int enable)
+{
+    if (!c) return fail(PZ_ERR_ARG, "null context");
+    c->profiling = enable != 0;
+    for (int i = 0; i < PZ_PHASES; ++i) { c->phase_ms[i] = 0; c->phase_launches[i] = 0; }
+    return PZ_OK;
+}
+
+int pz_profile_read(pz_ctx *c, double *ms_out, int64_t *launches_out)
+{
+    if (!c || !ms_out || !launches_out) return fail(PZ_ERR_ARG, "pz_profile_read: bad arguments");
+    for (int i = 0; i < PZ_PHASES; ++i) { ms_out[i] = c->phase_ms[i]; launches_out[i] = c->phase_launches[i]; }
+    return PZ_OK;
+}
+
+}  // extern "C"

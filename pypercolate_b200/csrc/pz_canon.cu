@@ -1,3 +1,332 @@
-// pz_canon.cu -- placeholder (binomial pmf / contraction kernels land next)
+// pz_canon.cu -- canonical ensemble: binomial weights and the contractions
+// with them (fp64, CUDA cores; sm_100a).
+//
+//   binomial_pmf      _binomial_pmf, percolate/percolate.py:1067-1109
+//   convolve          canonical_averages, percolate/percolate.py:1196-1221
+//   canon_rows        bond_canonical_statistics on host rows, percolate/hpc.py:488-515
+//   canon_runs        the same contraction for every run of a batch straight
+//                     from the merge records (nothing per-run materialised)
+//   canon_reduce      bond_initialize_canonical_averages + bond_reduce over the
+//                     runs of a batch, percolate/hpc.py:607-635, 664-702
 #include "pz_common.cuh"
 #include "pz_internal.h"
+
+namespace pz {
+
+// ---------------------------------------------------------------------------
+// _binomial_pmf: one thread per (p, direction).  The recurrence is evaluated
+// in the reference's operation order with explicitly rounded multiplies and
+// divides (no contraction), so every un-normalised weight is bit-identical to
+// the reference's; only the normalising sum is associated differently.
+// ---------------------------------------------------------------------------
+__global__ void binomial_pmf_kernel(int32_t M, int32_t P, const double *ps, double *pmf)
+{
+    const int pi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pi >= P) return;
+    const double p = ps[pi];
+    const double n = (double)M;
+    const long long nmax = (long long)rint(p * n);          // np.round: half to even
+    double *ret = pmf + (size_t)pi * ((size_t)M + 1);
+    if (blockIdx.y == 0) {
+        double v = 1.0;
+        ret[nmax] = v;
+        const double q = 1.0 - p;
+        for (long long i = nmax + 1; i <= M; ++i) {
+            // ret[i] = ret[i-1] * (n - i + 1.0) / i * p / (1.0 - p)
+            v = __ddiv_rn(__dmul_rn(__ddiv_rn(__dmul_rn(v, n - (double)i + 1.0), (double)i), p), q);
+            ret[i] = v;
+        }
+    } else {
+        double v = 1.0;
+        const double q = 1.0 - p;
+        for (long long i = nmax - 1; i >= 0; --i) {
+            // ret[i] = ret[i+1] * (i + 1.0) / (n - i) * (1.0 - p) / p
+            v = __ddiv_rn(__dmul_rn(__ddiv_rn(__dmul_rn(v, (double)i + 1.0), (double)(M - i)), q), p);
+            ret[i] = v;
+        }
+    }
+}
+
+__device__ __forceinline__ double block_sum(double v, double *sh)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = 16; k > 0; k >>= 1) v += __shfl_xor_sync(0xffffffffu, v, k);
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+    return t;
+}
+
+// normalise (ret / ret.sum()) and find the band [lo, hi] outside which the
+// weight is exactly zero (underflowed), so that banded sums drop no term
+static constexpr double PMF_EPS = 0.0;   // every non-zero weight is kept
+__global__ void __launch_bounds__(256) pmf_normalize_kernel(int32_t M, double *pmf, int32_t *band_lo,
+                                                             int32_t *band_hi)
+{
+    __shared__ double sh[8];
+    __shared__ int s_lo, s_hi;
+    double *ret = pmf + (size_t)blockIdx.x * ((size_t)M + 1);
+    // chunked partial sums keep the association close to a pairwise sum
+    double part = 0.0;
+    for (int i = threadIdx.x; i <= M; i += blockDim.x) part += ret[i];
+    const double s = block_sum(part, sh);
+    if (threadIdx.x == 0) { s_lo = M; s_hi = 0; }
+    __syncthreads();
+    int lo = M, hi = 0;
+    for (int i = threadIdx.x; i <= M; i += blockDim.x) {
+        const double v = __ddiv_rn(ret[i], s);
+        ret[i] = v;
+        if (v > PMF_EPS) { lo = min(lo, i); hi = max(hi, i); }
+    }
+    atomicMin(&s_lo, lo);
+    atomicMax(&s_hi, hi);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        band_lo[blockIdx.x] = min(s_lo, s_hi);
+        band_hi[blockIdx.x] = max(s_lo, s_hi);
+    }
+}
+
+cudaError_t launch_binomial_pmf(int32_t M, int32_t P, const double *ps_dev, double *pmf,
+                                int32_t *band_lo, int32_t *band_hi, cudaStream_t s)
+{
+    if (P <= 0) return cudaSuccess;
+    dim3 grid((P + 31) / 32, 2);
+    binomial_pmf_kernel<<<grid, 32, 0, s>>>(M, P, ps_dev, pmf);
+    pmf_normalize_kernel<<<P, 256, 0, s>>>(M, pmf, band_lo, band_hi);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// out[c][p] = sum_n pmf[p][n] * cols[c][n]   (one CTA per (p, c))
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) convolve_kernel(int32_t M, int32_t P, const double *pmf,
+                                                        const int32_t *band_lo, const int32_t *band_hi,
+                                                        const double *cols, double *out)
+{
+    __shared__ double sh[8];
+    const int p = blockIdx.x, c = blockIdx.y;
+    const double *f = pmf + (size_t)p * ((size_t)M + 1);
+    const double *x = cols + (size_t)c * ((size_t)M + 1);
+    double part = 0.0;
+    for (int i = band_lo[p] + threadIdx.x; i <= band_hi[p]; i += blockDim.x)
+        part += __dmul_rn(f[i], x[i]);
+    const double s = block_sum(part, sh);
+    if (threadIdx.x == 0) out[(size_t)c * P + p] = s;
+}
+
+cudaError_t launch_convolve(int32_t M, int32_t P, const double *pmf, const int32_t *band_lo,
+                            const int32_t *band_hi, int32_t num_cols, const double *cols,
+                            double *out, cudaStream_t s)
+{
+    if (P <= 0 || num_cols <= 0) return cudaSuccess;
+    dim3 grid(P, num_cols);
+    convolve_kernel<<<grid, 256, 0, s>>>(M, P, pmf, band_lo, band_hi, cols, out);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// bond_canonical_statistics on packed host rows of ONE run (hpc.py:488-515)
+// ---------------------------------------------------------------------------
+template <bool SPANNING>
+__global__ void __launch_bounds__(256) canon_rows_kernel(int32_t M, const uint8_t *rows,
+                                                          const double *f, double *out)
+{
+    constexpr int RB = SPANNING ? 53 : 52;
+    constexpr int MOFF = SPANNING ? 9 : 8;
+    __shared__ double sh[8];
+    double acc[7];
+#pragma unroll
+    for (int q = 0; q < 7; ++q) acc[q] = 0.0;
+    for (int i = threadIdx.x; i <= M; i += blockDim.x) {
+        const uint8_t *r = rows + (size_t)i * RB;
+        const double w = f[i];
+        if (SPANNING) acc[0] += __dmul_rn(w, (double)r[8]);
+        uint32_t mx = 0;
+        for (int b = 0; b < 4; ++b) mx |= (uint32_t)r[MOFF + b] << (8 * b);
+        acc[1] += __dmul_rn(w, (double)mx);
+        for (int k = 0; k < 5; ++k) {
+            uint64_t m = 0;
+            for (int b = 0; b < 8; ++b) m |= (uint64_t)r[MOFF + 4 + 8 * k + b] << (8 * b);
+            acc[2 + k] += __dmul_rn(w, (double)m);
+        }
+    }
+    for (int q = 0; q < 7; ++q) {
+        const double s = block_sum(acc[q], sh);
+        if (threadIdx.x == 0) out[q] = s;
+    }
+}
+
+cudaError_t launch_canon_rows(int32_t M, int spanning, const uint8_t *rows, const double *f,
+                              double *out, cudaStream_t s)
+{
+    if (spanning) canon_rows_kernel<true><<<1, 256, 0, s>>>(M, rows, f, out);
+    else canon_rows_kernel<false><<<1, 256, 0, s>>>(M, rows, f, out);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// canon_runs: out[run][p][7] = sum_n pmf_p[n] * Q_run[n] for all runs of a
+// batch, straight from the merge records.
+//
+// One lane owns one run (a warp = 32 runs in lock step), one warp owns a chunk
+// of PC probabilities whose weights live in 7*PC register accumulators.  The
+// warp starts at the last checkpoint (run state every `ckpt_every` rows, left
+// by accumulate_kernel) before the chunk's band and walks to its end; pmf
+// loads are warp-uniform.  Records go through the same padded tile as in
+// accumulate_kernel.
+// ---------------------------------------------------------------------------
+static constexpr int PC = 4;
+
+template <class RecT>
+__global__ void __launch_bounds__(128) canon_runs_kernel(StatsArgs a, int32_t P, int32_t nchunks,
+                                                          const double *pmf, const int32_t *band_lo,
+                                                          const int32_t *band_hi, const int32_t *porder,
+                                                          const RunState *ckpt, int ckpt_every,
+                                                          int n_ckpt, double *out)
+{
+    constexpr int TILE = sizeof(RecT) == 4 ? 32 : 16;
+    __shared__ RecT tile_all[4][32][TILE + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    RecT (*tile)[TILE + 1] = tile_all[warp];
+    const long long wid = (long long)blockIdx.x * 4 + warp;
+    const int rg = (int)(wid / nchunks), ch = (int)(wid % nchunks);
+    const int run0 = rg * 32;
+    if (run0 >= a.R) return;
+    const int run = run0 + lane;
+    const bool live = run < a.R;
+    const int M = a.M;
+    const size_t S = (size_t)M + 1;
+    const RecT *recs = reinterpret_cast<const RecT *>(a.recs);
+
+    // chunk band (sorted-p order)
+    const int p0 = ch * PC, np = min(PC, P - p0);
+    int lo = M, hi = 0;
+    int plo[PC], phi[PC];
+#pragma unroll
+    for (int k = 0; k < PC; ++k) {
+        plo[k] = k < np ? band_lo[p0 + k] : M + 1;
+        phi[k] = k < np ? band_hi[p0 + k] : -1;
+        if (k < np) { lo = min(lo, plo[k]); hi = max(hi, phi[k]); }
+    }
+    const int ck = lo / ckpt_every;                 // checkpoint row = ck * ckpt_every <= lo
+    const int row_start = ck * ckpt_every;          // state is the one AFTER this row
+    RunState st;
+    st.init((uint32_t)a.N);
+    if (live) st = ckpt[(size_t)run * n_ckpt + ck];
+    const uint32_t nspan = (live && a.spanning) ? a.nspan[run] : NSPAN_NEVER;
+
+    double acc[PC][7];
+#pragma unroll
+    for (int k = 0; k < PC; ++k)
+#pragma unroll
+        for (int q = 0; q < 7; ++q) acc[k][q] = 0.0;
+
+    double x[7];
+    bool dirty = true;
+    auto contribute = [&](int n) {
+        if (dirty) {
+            uint64_t m[5];
+            st.moments((uint32_t)a.N, m);
+            x[0] = (uint32_t)n >= nspan ? 1.0 : 0.0;
+            x[1] = (double)st.mx;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) x[2 + k] = (double)m[k];
+            dirty = false;
+        }
+#pragma unroll
+        for (int k = 0; k < PC; ++k) {
+            if (n >= plo[k] && n <= phi[k]) {
+                const double f = __ldg(&pmf[(size_t)(p0 + k) * S + n]);
+#pragma unroll
+                for (int q = 0; q < 7; ++q) acc[k][q] = fma(f, x[q], acc[k][q]);
+            }
+        }
+    };
+
+    // rows row_start .. hi; the state after row_start comes from the checkpoint,
+    // row n >= 1 applies record n-1
+    int row = row_start;
+    if (row >= lo) contribute(row);
+    while (row < hi) {
+        __syncwarp();
+        if (lane < TILE) {
+            const int idx = row + lane;           // record idx belongs to row idx+1
+            for (int rr = 0; rr < 32; ++rr) {
+                RecT v = 0;
+                if (run0 + rr < a.R && idx < M) v = __ldg(&recs[(size_t)(run0 + rr) * M + idx]);
+                tile[rr][lane] = v;
+            }
+        }
+        __syncwarp();
+        const int cnt = min(TILE, hi - row);
+        for (int j = 0; j < cnt; ++j) {
+            const RecT r = tile[lane][j];
+            const int nrow = row + 1 + j;
+            if (RecCodec<RecT>::valid(r)) {
+                st.merge(RecCodec<RecT>::w_small(r), RecCodec<RecT>::w_large(r));
+                dirty = true;
+            }
+            if ((uint32_t)nrow == nspan) dirty = true;
+            if (nrow >= lo) contribute(nrow);
+        }
+        row += cnt;
+    }
+    if (live) {
+        for (int k = 0; k < np; ++k) {
+            double *o = out + ((size_t)run * P + porder[p0 + k]) * 7;
+            for (int q = 0; q < 7; ++q) o[q] = acc[k][q];
+        }
+    }
+}
+
+cudaError_t launch_canon_runs(const StatsArgs &a, int32_t P, const double *pmf,
+                              const int32_t *band_lo, const int32_t *band_hi, const int32_t *porder,
+                              const RunState *ckpt, int ckpt_every, int n_ckpt, double *out,
+                              cudaStream_t s)
+{
+    if (a.R <= 0 || P <= 0) return cudaSuccess;
+    const int nchunks = (P + PC - 1) / PC;
+    const long long warps = (long long)((a.R + 31) / 32) * nchunks;
+    const int grid = (int)((warps + 3) / 4);
+    if (a.rec64)
+        canon_runs_kernel<uint64_t><<<grid, 128, 0, s>>>(a, P, nchunks, pmf, band_lo, band_hi, porder,
+                                                          ckpt, ckpt_every, n_ckpt, out);
+    else
+        canon_runs_kernel<uint32_t><<<grid, 128, 0, s>>>(a, P, nchunks, pmf, band_lo, band_hi, porder,
+                                                          ckpt, ckpt_every, n_ckpt, out);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// canon_reduce: (mean, M2) over the R runs of a batch for each of P*7 columns
+// (two-pass, fixed association -> deterministic)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) canon_reduce_kernel(int32_t R, int32_t cols, const double *runs,
+                                                            double *mean, double *m2)
+{
+    __shared__ double sh[8];
+    const int c = blockIdx.x;
+    double part = 0.0;
+    for (int r = threadIdx.x; r < R; r += blockDim.x) part += runs[(size_t)r * cols + c];
+    const double mu = block_sum(part, sh) / (double)R;
+    part = 0.0;
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        const double d = runs[(size_t)r * cols + c] - mu;
+        part += d * d;
+    }
+    const double s2 = block_sum(part, sh);
+    if (threadIdx.x == 0) { mean[c] = mu; m2[c] = s2; }
+}
+
+cudaError_t launch_canon_reduce(int32_t R, int32_t cols, const double *runs, double *mean,
+                                double *m2, cudaStream_t s)
+{
+    if (R <= 0 || cols <= 0) return cudaSuccess;
+    canon_reduce_kernel<<<cols, 256, 0, s>>>(R, cols, runs, mean, m2);
+    return cudaGetLastError();
+}
+
+}  // namespace pz

@@ -1,10 +1,286 @@
-// pz_rng.cu -- bond orders generated on the device (placeholder until the
-// Philox / MT19937 kernels land).
+// pz_rng.cu -- bond orders generated on the device (sm_100a).
+//
+// The reference draws the bond order of a run on the host,
+// ``RandomState(seed).permutation(M)`` (percolate/hpc.py:195,206).  Two device
+// replacements:
+//
+//  * perm_mt19937: NumPy's legacy stream reproduced bit for bit -- MT19937
+//    seeded by init_genrand(seed), then the legacy shuffle (for i = M-1..1:
+//    j = masked-rejection draw in [0, i]; swap).  One thread per run; the
+//    twister state lives in thread-local memory, the permutation in the run's
+//    row of the output (HBM-resident, latency hidden by running every run of
+//    the batch concurrently).
+//
+//  * perm_philox: counter-based Philox4x32-10.  A uniform permutation is built
+//    in two exact steps (Rao-Sandelius): every bond draws one of B buckets
+//    uniformly and is placed by a STABLE counting sort (so the result does not
+//    depend on thread timing), then every bucket is shuffled by Fisher-Yates in
+//    shared memory with unbiased (Lemire) bounded draws.  One CTA per run.
+//    Counters: bucket draws (i >> 2, 0, 0, 0) lane i & 3; Fisher-Yates draws
+//    (step, bucket, attempt, 1).  Key: (seed, 0x50455243).
+//    oracle/pz_oracle.c restates this algorithm on the CPU for bit-exact tests.
 #include "pz_common.cuh"
 #include "pz_internal.h"
+
 namespace pz {
-cudaError_t launch_perm_philox(int32_t, int32_t, const uint32_t *, int32_t *, cudaStream_t, int *)
-{ return cudaErrorNotSupported; }
-cudaError_t launch_perm_mt19937(int32_t, int32_t, const uint32_t *, int32_t *, cudaStream_t, int *)
-{ return cudaErrorNotSupported; }
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0,
+                                                       uint32_t c1, uint32_t c2, uint32_t c3,
+                                                       uint32_t out[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        const uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
+
+static constexpr uint32_t PHILOX_KEY1 = 0x50455243u;   // 'PERC'
+static constexpr int PH_THREADS = 256;
+static constexpr int PH_WARPS = PH_THREADS / 32;
+
+__device__ __forceinline__ uint32_t philox_bucket(uint32_t seed, uint32_t i, uint32_t bmask)
+{
+    uint32_t o[4];
+    philox4x32_10(seed, PHILOX_KEY1, i >> 2, 0u, 0u, 0u, o);
+    return o[i & 3u] & bmask;
+}
+
+// unbiased j in [0, k] (Lemire), draws taken from counter (step, bucket, attempt, 1)
+__device__ __forceinline__ uint32_t philox_bounded(uint32_t seed, uint32_t step, uint32_t bucket,
+                                                   uint32_t k)
+{
+    const uint32_t range = k + 1u;
+    const uint32_t thresh = (0u - range) % range;
+    uint32_t attempt = 0;
+    for (;;) {
+        uint32_t o[4];
+        philox4x32_10(seed, PHILOX_KEY1, step, bucket, attempt, 1u, o);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint64_t m = (uint64_t)o[q] * range;
+            if ((uint32_t)m >= thresh) return (uint32_t)(m >> 32);
+        }
+        ++attempt;
+    }
+}
+
+struct PhiloxPlan {
+    int log2_buckets;
+    int cap;             // shared-memory capacity (entries) of one bucket in the shuffle phase
+    int fy_threads;
+    size_t smem_bytes;
+};
+
+static PhiloxPlan plan_philox(int32_t M)
+{
+    PhiloxPlan p{};
+    int lb = 0;
+    while (lb < 11 && ((long long)64 << lb) < M) ++lb;      // mean bucket ~64 until B = 2048
+    p.log2_buckets = lb;
+    const double mean = (double)M / (double)(1 << lb);
+    int cap = (int)(mean + 8.0 * sqrt(mean) + 16.0);
+    cap |= 1;                                               // odd stride: no systematic bank conflicts
+    const size_t budget = 144 * 1024;
+    int t = (int)(budget / ((size_t)cap * 4));
+    if (t > PH_THREADS) t = PH_THREADS;
+    if (t < 1) t = 1;
+    p.cap = cap;
+    p.fy_threads = t;
+    const size_t hist = (size_t)(PH_WARPS + 1) * ((size_t)1 << lb) * 4 + 64;
+    const size_t fy = (size_t)t * cap * 4 + ((size_t)(1 << lb) + 1) * 4;
+    p.smem_bytes = hist > fy ? hist : fy;
+    p.smem_bytes += ((size_t)(1 << lb) + 1) * 4;            // bucket starts survive both phases
+    return p;
+}
+
+__global__ void __launch_bounds__(PH_THREADS) perm_philox_kernel(int32_t M, int32_t R,
+                                                                  const uint32_t *seeds, int32_t *perms,
+                                                                  int log2b, int cap, int fy_threads)
+{
+    extern __shared__ __align__(16) uint32_t sm[];
+    const int B = 1 << log2b;
+    const uint32_t bmask = (uint32_t)B - 1u;
+    uint32_t *start = sm;                       // [B + 1]
+    uint32_t *hist = sm + B + 1;                // [PH_WARPS][B] then per-warp bases
+    uint32_t *fybuf = sm + B + 1;               // [fy_threads][cap]   (after the scatter)
+    __shared__ uint32_t scan_tot[PH_WARPS];
+
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    // contiguous element range of this warp (multiple of 32)
+    const int per_warp = (((M + PH_WARPS - 1) / PH_WARPS) + 31) & ~31;
+    const int w_lo = min(M, warp * per_warp), w_hi = min(M, w_lo + per_warp);
+
+    for (int run = blockIdx.x; run < R; run += gridDim.x) {
+        const uint32_t seed = seeds[run];
+        int32_t *out = perms + (size_t)run * M;
+
+        // ---- A: per-warp histograms of the bucket draws ----------------------
+        for (int i = t; i < PH_WARPS * B; i += PH_THREADS) hist[i] = 0;
+        __syncthreads();
+        for (int i = w_lo + lane; i < w_hi; i += 32)
+            atomicAdd(&hist[warp * B + philox_bucket(seed, (uint32_t)i, bmask)], 1u);
+        __syncthreads();
+
+        // ---- A': bucket starts (exclusive scan) and per-warp bases -----------
+        {
+            // thread t owns buckets [t*per, (t+1)*per)
+            const int per = (B + PH_THREADS - 1) / PH_THREADS;
+            const int b_lo = min(B, t * per), b_hi = min(B, b_lo + per);
+            uint32_t mine = 0;
+            for (int b = b_lo; b < b_hi; ++b)
+                for (int w = 0; w < PH_WARPS; ++w) mine += hist[w * B + b];
+            uint32_t incl = mine;
+            for (int k = 1; k < 32; k <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, k);
+                if (lane >= k) incl += o;
+            }
+            if (lane == 31) scan_tot[warp] = incl;
+            __syncthreads();
+            uint32_t pre = incl - mine;
+            for (int w = 0; w < warp; ++w) pre += scan_tot[w];
+            for (int b = b_lo; b < b_hi; ++b) {
+                start[b] = pre;
+                uint32_t run_base = pre;
+                for (int w = 0; w < PH_WARPS; ++w) {
+                    const uint32_t h = hist[w * B + b];
+                    hist[w * B + b] = run_base;
+                    run_base += h;
+                }
+                pre = run_base;
+            }
+            if (t == PH_THREADS - 1) start[B] = (uint32_t)M;
+        }
+        __syncthreads();
+
+        // ---- B: stable scatter (order inside a bucket = ascending bond index) --
+        for (int i0 = w_lo; i0 < w_hi; i0 += 32) {
+            const int i = i0 + lane;
+            const bool valid = i < w_hi;
+            const uint32_t b = valid ? philox_bucket(seed, (uint32_t)i, bmask) : 0xffffffffu;
+            const uint32_t peers = __match_any_sync(0xffffffffu, b);
+            const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+            uint32_t pos = 0;
+            if (valid) pos = hist[warp * B + b] + rank;
+            __syncwarp();
+            if (valid && rank == 0) hist[warp * B + b] += __popc(peers);
+            __syncwarp();
+            if (valid) out[pos] = i;
+        }
+        __syncthreads();
+
+        // ---- C: Fisher-Yates inside every bucket, in shared memory -------------
+        for (int b0 = 0; b0 < B; b0 += fy_threads) {
+            const int b = b0 + t;
+            if (t < fy_threads && b < B) {
+                const uint32_t s0 = start[b], sz = start[b + 1] - s0;
+                if (sz > 1) {
+                    if ((int)sz <= cap) {
+                        uint32_t *buf = fybuf + (size_t)t * cap;
+                        for (uint32_t k = 0; k < sz; ++k) buf[k] = (uint32_t)out[s0 + k];
+                        for (uint32_t k = sz - 1; k >= 1; --k) {
+                            const uint32_t j = philox_bounded(seed, k, (uint32_t)b, k);
+                            const uint32_t a = buf[k], c = buf[j];
+                            buf[k] = c; buf[j] = a;
+                        }
+                        for (uint32_t k = 0; k < sz; ++k) out[s0 + k] = (int32_t)buf[k];
+                    } else {                      // over-full bucket: same shuffle in place
+                        for (uint32_t k = sz - 1; k >= 1; --k) {
+                            const uint32_t j = philox_bounded(seed, k, (uint32_t)b, k);
+                            const int32_t a = out[s0 + k], c = out[s0 + j];
+                            out[s0 + k] = c; out[s0 + j] = a;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_perm_philox(int32_t M, int32_t R, const uint32_t *seeds, int32_t *perms,
+                               cudaStream_t s, int *launches)
+{
+    *launches = 0;
+    if (R <= 0 || M <= 0) return cudaSuccess;
+    const PhiloxPlan p = plan_philox(M);
+    cudaError_t e = cudaFuncSetAttribute(perm_philox_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)p.smem_bytes);
+    if (e != cudaSuccess) return e;
+    perm_philox_kernel<<<R, PH_THREADS, p.smem_bytes, s>>>(M, R, seeds, perms, p.log2_buckets, p.cap,
+                                                           p.fy_threads);
+    *launches = 1;
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// NumPy legacy stream: MT19937 + masked-rejection Fisher-Yates
+// ---------------------------------------------------------------------------
+__global__ void iota_rows_kernel(int32_t M, int32_t R, int32_t *perms)
+{
+    const size_t total = (size_t)M * R;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x)
+        perms[i] = (int32_t)(i % (size_t)M);
+}
+
+__global__ void __launch_bounds__(64) perm_mt19937_kernel(int32_t M, int32_t R, const uint32_t *seeds,
+                                                           int32_t *perms)
+{
+    const int run = blockIdx.x * blockDim.x + threadIdx.x;
+    if (run >= R) return;
+    uint32_t mt[624];
+    {
+        uint32_t v = seeds[run];
+        mt[0] = v;
+        for (int i = 1; i < 624; ++i) { v = 1812433253u * (v ^ (v >> 30)) + (uint32_t)i; mt[i] = v; }
+    }
+    int idx = 624;
+    int32_t *x = perms + (size_t)run * M;
+    for (int32_t i = M - 1; i >= 1; --i) {
+        uint32_t mask = (uint32_t)i;
+        mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+        uint32_t j;
+        do {
+            if (idx >= 624) {
+                for (int k = 0; k < 624; ++k) {
+                    const uint32_t y = (mt[k] & 0x80000000u) | (mt[k == 623 ? 0 : k + 1] & 0x7fffffffu);
+                    mt[k] = mt[k + 397 < 624 ? k + 397 : k + 397 - 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+                }
+                idx = 0;
+            }
+            uint32_t y = mt[idx++];
+            y ^= (y >> 11);
+            y ^= (y << 7) & 0x9d2c5680u;
+            y ^= (y << 15) & 0xefc60000u;
+            y ^= (y >> 18);
+            j = y & mask;
+        } while (j > (uint32_t)i);
+        const int32_t a = x[i], b = x[j];
+        x[i] = b; x[j] = a;
+    }
+}
+
+cudaError_t launch_perm_mt19937(int32_t M, int32_t R, const uint32_t *seeds, int32_t *perms,
+                                cudaStream_t s, int *launches)
+{
+    *launches = 0;
+    if (R <= 0 || M <= 0) return cudaSuccess;
+    iota_rows_kernel<<<1184, 256, 0, s>>>(M, R, perms);
+    perm_mt19937_kernel<<<(R + 63) / 64, 64, 0, s>>>(M, R, seeds, perms);
+    *launches = 2;
+    return cudaGetLastError();
+}
+
+}  // namespace pz

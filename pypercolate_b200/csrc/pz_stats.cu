@@ -166,8 +166,8 @@ __global__ void __launch_bounds__(ROWS_THREADS) expand_rows_kernel(StatsArgs a, 
 //   4        sum c             5,6    sum c^2        (c = merges so far)
 //   7+6j..   j = 0,1,2 for moments[2+j] = m:
 //            sum m (lo32, hi32), sum m^2 (four 32-bit limbs)
-// Optionally writes the run state every CKPT rows (used by the per-run
-// canonical contraction to start in the middle of a run).
+// A warp covers one segment of rows of its 32 runs, starting from the run
+// states that checkpoint_kernel left at the segment boundary.
 // ===========================================================================
 static constexpr int ACC_WORDS = 25;
 
@@ -182,95 +182,142 @@ __device__ __forceinline__ void halve_step(uint64_t (&v)[32], int lane) {
     }
 }
 
-template <class RecT, bool ACCUM>
+// checkpoints: run state after every `every`-th row, by a block-wide scan
+// (one CTA per run) -- lets accumulate / canon_runs start anywhere in a run
+template <class RecT>
+__global__ void __launch_bounds__(ROWS_THREADS) checkpoint_kernel(StatsArgs a, RunState *ckpt,
+                                                                   int every, int n_ckpt)
+{
+    __shared__ Delta warp_tot[ROWS_THREADS / 32];
+    __shared__ Delta carry;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int run = blockIdx.x;
+    const RecT *recs = reinterpret_cast<const RecT *>(a.recs) + (size_t)run * a.M;
+    const int rows_total = a.M + 1;
+    if (t == 0) carry = Delta{0u, 1u, (uint64_t)a.N, (uint64_t)a.N, (uint64_t)a.N};
+    __syncthreads();
+    for (int n0 = 0; n0 < rows_total; n0 += ROWS_THREADS) {
+        const int n = n0 + t;
+        Delta d{0, 0, 0, 0, 0};
+        if (n < rows_total && n >= 1) d = delta_of<RecT>(__ldg(&recs[n - 1]));
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) {
+            Delta o = delta_shfl_up(d, k);
+            if (lane >= k) d = delta_combine(o, d);
+        }
+        if (lane == 31) warp_tot[warp] = d;
+        __syncthreads();
+        Delta pre = carry;
+        for (int w = 0; w < warp; ++w) pre = delta_combine(pre, warp_tot[w]);
+        d = delta_combine(pre, d);
+        __syncthreads();
+        if (t == ROWS_THREADS - 1) carry = d;
+        if (n < rows_total && (n % every) == 0) {
+            RunState st;
+            st.c = d.c; st.mx = d.mx; st.s2 = d.s2; st.s3 = d.s3; st.s4 = d.s4;
+            ckpt[(size_t)run * n_ckpt + n / every] = st;
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_checkpoints(const StatsArgs &a, RunState *ckpt, int every, int n_ckpt,
+                               cudaStream_t s)
+{
+    if (a.R <= 0) return cudaSuccess;
+    if (a.rec64) checkpoint_kernel<uint64_t><<<a.R, ROWS_THREADS, 0, s>>>(a, ckpt, every, n_ckpt);
+    else checkpoint_kernel<uint32_t><<<a.R, ROWS_THREADS, 0, s>>>(a, ckpt, every, n_ckpt);
+    return cudaGetLastError();
+}
+
+// one warp = (32 runs) x (one segment of `seg` rows starting at a checkpoint)
+template <class RecT>
 __global__ void __launch_bounds__(256) accumulate_kernel(StatsArgs a, unsigned long long *acc,
-                                                          RunState *ckpt, int ckpt_every, int n_ckpt)
+                                                          const RunState *ckpt, int seg, int n_ckpt)
 {
     constexpr int TILE = sizeof(RecT) == 4 ? 32 : 16;
     __shared__ RecT tile_all[8][32][TILE + 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     RecT (*tile)[TILE + 1] = tile_all[warp];
-    const int run0 = (blockIdx.x * 8 + warp) * 32;
+    const long long wid = (long long)blockIdx.x * 8 + warp;
+    const int sgi = (int)(wid % n_ckpt);                 // segment index
+    const int run0 = (int)(wid / n_ckpt) * 32;
     if (run0 >= a.R) return;
     const int run = run0 + lane;
     const bool live = run < a.R;
     const RecT *recs = reinterpret_cast<const RecT *>(a.recs);
     const int M = a.M;
+    const int row_lo = sgi * seg, row_hi = min(M, row_lo + seg - 1);   // rows of this segment
 
     RunState st;
     st.init((uint32_t)a.N);
-    if (ACCUM && live && a.spanning) {
+    if (live) st = ckpt[(size_t)run * n_ckpt + sgi];     // state AFTER row_lo
+    if (sgi == 0 && live && a.spanning) {
         const uint32_t ns = a.nspan[run];
         if (ns != NSPAN_NEVER) atomicAdd(&acc[(size_t)ns * ACC_WORDS + 0], 1ull);
     }
 
-    // rows n = 0..M; row n >= 1 applies record n-1
-    for (int r0 = 0; r0 <= M; r0 += TILE) {
-        // stage records r0-1 .. r0+TILE-2 of the 32 runs
+    auto emit = [&](int n) {
+        uint64_t v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0;
+        if (live) {
+            const uint64_t x = st.mx, x2 = x * x, c = st.c, c2 = c * c;
+            v[1] = x;
+            v[2] = x2 & 0xffffffffu; v[3] = x2 >> 32;
+            v[4] = c;
+            v[5] = c2 & 0xffffffffu; v[6] = c2 >> 32;
+            const uint64_t m[3] = {st.s2 - x2, st.s3 - x2 * x, st.s4 - x2 * x2};
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const uint64_t lo = m[k] * m[k], hi = __umul64hi(m[k], m[k]);
+                v[7 + 6 * k + 0] = m[k] & 0xffffffffu;
+                v[7 + 6 * k + 1] = m[k] >> 32;
+                v[7 + 6 * k + 2] = lo & 0xffffffffu;
+                v[7 + 6 * k + 3] = lo >> 32;
+                v[7 + 6 * k + 4] = hi & 0xffffffffu;
+                v[7 + 6 * k + 5] = hi >> 32;
+            }
+        }
+        halve_step<16>(v, lane);
+        halve_step<8>(v, lane);
+        halve_step<4>(v, lane);
+        halve_step<2>(v, lane);
+        halve_step<1>(v, lane);
+        if (lane >= 1 && lane < ACC_WORDS && v[0])
+            atomicAdd(&acc[(size_t)n * ACC_WORDS + lane], (unsigned long long)v[0]);
+    };
+
+    emit(row_lo);
+    for (int row = row_lo; row < row_hi; row += TILE) {
+        // records row .. row+TILE-1 produce rows row+1 .. row+TILE
         __syncwarp();
         if (lane < TILE) {
-            const int idx = r0 - 1 + lane;
+            const int idx = row + lane;
             for (int rr = 0; rr < 32; ++rr) {
                 RecT v = 0;
-                if (run0 + rr < a.R && idx >= 0 && idx < M)
-                    v = __ldcs(&recs[(size_t)(run0 + rr) * M + idx]);
+                if (run0 + rr < a.R && idx < M) v = __ldcs(&recs[(size_t)(run0 + rr) * M + idx]);
                 tile[rr][lane] = v;
             }
         }
         __syncwarp();
-        const int rows = min(TILE, M + 1 - r0);
-        for (int j = 0; j < rows; ++j) {
-            const int n = r0 + j;
+        const int cnt = min(TILE, row_hi - row);
+        for (int j = 0; j < cnt; ++j) {
             const RecT r = tile[lane][j];
             if (RecCodec<RecT>::valid(r)) st.merge(RecCodec<RecT>::w_small(r), RecCodec<RecT>::w_large(r));
-            if (ckpt && live && (n % ckpt_every) == 0)
-                ckpt[(size_t)run * n_ckpt + n / ckpt_every] = st;
-            if (ACCUM) {
-                uint64_t v[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = 0;
-                if (live) {
-                    const uint64_t x = st.mx, x2 = x * x, c = st.c, c2 = c * c;
-                    v[1] = x;
-                    v[2] = x2 & 0xffffffffu; v[3] = x2 >> 32;
-                    v[4] = c;
-                    v[5] = c2 & 0xffffffffu; v[6] = c2 >> 32;
-                    const uint64_t m[3] = {st.s2 - x2, st.s3 - x2 * x, st.s4 - x2 * x2};
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const uint64_t lo = m[k] * m[k], hi = __umul64hi(m[k], m[k]);
-                        v[7 + 6 * k + 0] = m[k] & 0xffffffffu;
-                        v[7 + 6 * k + 1] = m[k] >> 32;
-                        v[7 + 6 * k + 2] = lo & 0xffffffffu;
-                        v[7 + 6 * k + 3] = lo >> 32;
-                        v[7 + 6 * k + 4] = hi & 0xffffffffu;
-                        v[7 + 6 * k + 5] = hi >> 32;
-                    }
-                }
-                halve_step<16>(v, lane);
-                halve_step<8>(v, lane);
-                halve_step<4>(v, lane);
-                halve_step<2>(v, lane);
-                halve_step<1>(v, lane);
-                if (lane >= 1 && lane < ACC_WORDS && v[0])
-                    atomicAdd(&acc[(size_t)n * ACC_WORDS + lane], (unsigned long long)v[0]);
-            }
+            emit(row + 1 + j);
         }
     }
 }
 
-cudaError_t launch_accumulate(const StatsArgs &a, unsigned long long *acc, RunState *ckpt,
-                              int ckpt_every, int n_ckpt, cudaStream_t s)
+cudaError_t launch_accumulate(const StatsArgs &a, unsigned long long *acc, const RunState *ckpt,
+                              int seg, int n_ckpt, cudaStream_t s)
 {
     if (a.R <= 0) return cudaSuccess;
-    const int grid = (a.R + 255) / 256;
-    if (acc) {
-        if (a.rec64) accumulate_kernel<uint64_t, true><<<grid, 256, 0, s>>>(a, acc, ckpt, ckpt_every, n_ckpt);
-        else accumulate_kernel<uint32_t, true><<<grid, 256, 0, s>>>(a, acc, ckpt, ckpt_every, n_ckpt);
-    } else {
-        if (a.rec64) accumulate_kernel<uint64_t, false><<<grid, 256, 0, s>>>(a, acc, ckpt, ckpt_every, n_ckpt);
-        else accumulate_kernel<uint32_t, false><<<grid, 256, 0, s>>>(a, acc, ckpt, ckpt_every, n_ckpt);
-    }
+    const long long warps = (long long)((a.R + 31) / 32) * n_ckpt;
+    const int grid = (int)((warps + 7) / 8);
+    if (a.rec64) accumulate_kernel<uint64_t><<<grid, 256, 0, s>>>(a, acc, ckpt, seg, n_ckpt);
+    else accumulate_kernel<uint32_t><<<grid, 256, 0, s>>>(a, acc, ckpt, seg, n_ckpt);
     return cudaGetLastError();
 }
 

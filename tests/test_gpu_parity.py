@@ -1,0 +1,496 @@
+"""Parity of the CUDA path (through the C-ABI / the public Python API) with the
+reference: golden vectors produced by the unmodified reference, the CPU
+oracle on seeded inputs, and size-independent properties at full size.
+
+Bars: integer work (rows, sums, permutations) bit-exact; floating point within
+1e-10 relative (RTOL) unless a looser bound is stated next to the assertion
+with its reason."""
+import functools
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import (ATOL, HPC_FIXTURES, ORIG_FIXTURES, RTOL, assert_rows_equal, golden_graph,
+                      golden_rows, load_golden, row_dtype)
+
+pytestmark = pytest.mark.gpu
+
+
+def _native():
+    from pypercolate_b200 import _native
+    return _native
+
+
+def ctx_for(g, force=None):
+    n = _native()
+    if force is None:
+        os.environ.pop("PZ_FORCE_STORE", None)
+    else:
+        os.environ["PZ_FORCE_STORE"] = str(force)
+    try:
+        ctx = n.Context(0)
+    finally:
+        os.environ.pop("PZ_FORCE_STORE", None)
+    ctx.set_graph(g)
+    return ctx
+
+
+# ---------------------------------------------------------------------------
+# rows: bond_sample_states / bond_microcanonical_statistics
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("force", [None, 1, 2])
+@pytest.mark.parametrize("name", HPC_FIXTURES)
+def test_rows_match_reference_golden(name, force):
+    n = _native()
+    d = load_golden(name)
+    g = golden_graph(d)
+    ctx = ctx_for(g, force)
+    ref = golden_rows(d)
+    # exact mode: the reference's own bond orders, supplied by the host
+    rows = ctx.run_rows(ref.shape[0], n.PERM_HOST, d['perms'])
+    assert_rows_equal(rows, ref, name + " host perms")
+    # seeds only: numpy's legacy stream reproduced on the device
+    rows, perms = ctx.run_rows(ref.shape[0], n.PERM_MT19937, d['seeds'].astype(np.uint32),
+                               want_perms=True)
+    assert np.array_equal(perms, d['perms'])
+    assert_rows_equal(rows, ref, name + " device mt19937")
+    assert ctx.launch_count > 0
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", ["big_grid64", "big_grid128"])
+def test_large_single_runs_match_reference_digest(name):
+    from pypercolate_b200 import lowering
+    n = _native()
+    d = load_golden(name)
+    g = lowering.lowered_spanning_2d_grid(int(d['L']))
+    ctx = ctx_for(g)
+    rows = ctx.run_rows(len(d['seeds']), n.PERM_MT19937, d['seeds'].astype(np.uint32))
+    for r in range(len(d['seeds'])):
+        b = rows[r].copy()
+        b['edge'][0] = 0
+        raw = b.view(np.uint8)
+        assert np.array_equal(raw.reshape(g.num_edges + 1, -1)[::499], d['sample_rows'][r])
+        assert hashlib.sha256(raw.tobytes()).digest() == d['sha256'][r].tobytes()
+    ctx.close()
+
+
+@pytest.mark.parametrize("force", [None, 2])
+@pytest.mark.parametrize("kind,L,runs", [("2d", 32, 48), ("2d", 128, 40), ("2d", 181, 6),
+                                         ("2d", 256, 6), ("3d", 20, 8), ("chain", 200, 5)])
+def test_rows_match_oracle(kind, L, runs, force):
+    from pypercolate_b200 import lowering
+    from oracle import oracle
+    n = _native()
+    g = {"2d": lowering.lowered_spanning_2d_grid, "3d": lowering.lowered_spanning_3d_grid,
+         "chain": lowering.lowered_spanning_1d_chain}[kind](L)
+    ctx = ctx_for(g, force)
+    seeds = np.arange(runs, dtype=np.uint32) * 7919 + 13
+    rows = ctx.run_rows(runs, n.PERM_MT19937, seeds)
+    for r in range(runs):
+        ref = oracle.sweep_rows(g.num_nodes, g.num_edges, g.eu, g.ev, g.side_mask,
+                                g.preconnected, oracle.numpy_permutation(int(seeds[r]), g.num_edges))
+        assert_rows_equal(rows[r], ref, "%s L=%d run %d" % (kind, L, r))
+    ctx.close()
+
+
+def test_rows_without_spanning_and_ragged_inputs():
+    from pypercolate_b200 import lowering
+    from oracle import oracle
+    n = _native()
+    # self loops, multi-edges, isolated nodes, empty bond list, zero runs
+    g = lowering.LoweredGraph(7, [0, 1, 1, 2, 3, 3], [1, 0, 1, 3, 2, 4])
+    ctx = ctx_for(g)
+    perms = np.stack([np.random.RandomState(s).permutation(6) for s in range(9)]).astype(np.int32)
+    rows = ctx.run_rows(9, n.PERM_HOST, perms)
+    assert rows.dtype.itemsize == 52
+    for r in range(9):
+        assert_rows_equal(rows[r], oracle.sweep_rows(7, 6, g.eu, g.ev, None, False, perms[r]))
+    assert ctx.run_rows(0, n.PERM_HOST, np.zeros((0, 6), np.int32)).shape == (0, 7)
+    ctx.close()
+    g0 = lowering.LoweredGraph(3, [], [], side_mask=[1, 0, 2])
+    ctx = ctx_for(g0)
+    rows = ctx.run_rows(2, n.PERM_HOST, np.zeros((2, 0), np.int32))
+    assert rows.shape == (2, 1) and rows['max_cluster_size'].tolist() == [[1], [1]]
+    assert rows['moments'][0, 0].tolist() == [2] * 5
+    ctx.close()
+
+
+def test_philox_bond_orders_match_restatement():
+    from pypercolate_b200 import lowering
+    from oracle import oracle
+    n = _native()
+    for L in (3, 8, 32, 128, 256):
+        g = lowering.lowered_spanning_2d_grid(L)
+        ctx = ctx_for(g)
+        seeds = np.array([0, 1, 42, 2 ** 32 - 1, 99], dtype=np.uint32)
+        perms = ctx.make_perms(seeds.size, n.PERM_PHILOX, seeds)
+        for r, s in enumerate(seeds):
+            assert np.array_equal(perms[r], oracle.philox_permutation(int(s), g.num_edges))
+        ctx.close()
+
+
+# ---------------------------------------------------------------------------
+# fused reduction over runs
+# ---------------------------------------------------------------------------
+def exact_sums(rows, N):
+    mx = np.stack([r['max_cluster_size'] for r in rows]).astype(object)
+    mom = np.stack([r['moments'] for r in rows]).astype(object)
+    return mx, mom
+
+
+@pytest.mark.parametrize("force", [None, 2])
+@pytest.mark.parametrize("kind,L,runs", [("2d", 8, 70), ("2d", 32, 40), ("3d", 6, 33), ("2d", 40, 300)])
+def test_micro_accumulators_are_exact(kind, L, runs, force):
+    from pypercolate_b200 import lowering
+    from oracle import oracle
+    n = _native()
+    g = (lowering.lowered_spanning_2d_grid if kind == "2d" else lowering.lowered_spanning_3d_grid)(L)
+    N, M = g.num_nodes, g.num_edges
+    ctx = ctx_for(g, force)
+    perms = np.stack([oracle.numpy_permutation(500 + r, M) for r in range(runs)])
+    rows = [oracle.sweep_rows(N, M, g.eu, g.ev, g.side_mask, g.preconnected, p) for p in perms]
+    # two calls accumulate
+    half = runs // 2
+    ctx.run_fused(half, n.PERM_HOST, perms[:half], n.FUSE_MICRO)
+    ctx.run_fused(runs - half, n.PERM_HOST, perms[half:], n.FUSE_MICRO)
+    assert ctx.micro_runs == runs
+    acc = ctx.micro_export()
+    mx, mom = exact_sums(rows, N)
+    span = np.stack([r['has_spanning_cluster'] for r in rows]).astype(np.int64)
+    assert np.array_equal(np.cumsum(acc[:, 0].astype(np.int64)), span.sum(axis=0))
+    step = max(1, (M + 1) // 200)
+    for i in list(range(0, M + 1, step)) + [M]:
+        w = [int(x) for x in acc[i]]
+        assert w[1] == sum(mx[:, i])
+        assert w[2] + (w[3] << 32) == sum(x * x for x in mx[:, i])
+        c = [(N - 1) - x for x in mom[:, i, 0]]
+        assert w[4] == sum(c) and w[5] + (w[6] << 32) == sum(x * x for x in c)
+        for k in range(3):
+            q = w[7 + 6 * k: 13 + 6 * k]
+            assert q[0] + (q[1] << 32) == sum(mom[:, i, 2 + k])
+            assert q[2] + (q[3] << 32) + (q[4] << 64) + (q[5] << 96) == \
+                sum(x * x for x in mom[:, i, 2 + k])
+    mean, var = ctx.micro_finalize()
+    fm = np.stack([r['max_cluster_size'] for r in rows]).astype(np.float64)
+    fmom = np.stack([r['moments'] for r in rows]).astype(np.float64)
+    assert np.array_equal(mean[0], span.sum(axis=0))
+    np.testing.assert_allclose(mean[1], fm.mean(axis=0), rtol=1e-13)
+    np.testing.assert_allclose(var[0], fm.var(axis=0, ddof=1), rtol=RTOL, atol=ATOL)
+    for k in range(5):
+        np.testing.assert_allclose(mean[2 + k], fmom[:, :, k].mean(axis=0), rtol=1e-13)
+        # numpy's two-pass variance itself carries ~1e-16 * mean^2 / var of error
+        np.testing.assert_allclose(var[1 + k], fmom[:, :, k].var(axis=0, ddof=1), rtol=1e-8, atol=ATOL)
+        assert np.array_equal(var[1 + k] == 0, np.ptp(fmom[:, :, k], axis=0) == 0)
+    # export / import round trip (the cross-GPU exchange)
+    ctx.reset_accumulators()
+    assert ctx.micro_runs == 0
+    ctx.micro_import(acc, runs)
+    assert np.array_equal(ctx.micro_export(), acc)
+    ctx.close()
+
+
+# ---------------------------------------------------------------------------
+# canonical ensemble
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name", [n for n in HPC_FIXTURES if n not in ("hpc_chain1", "hpc_preconnected")])
+def test_canonical_chain_matches_reference_golden(name):
+    from pypercolate_b200 import hpc
+    n = _native()
+    d = load_golden(name)
+    spanning = bool(int(d['spanning']))
+    g = golden_graph(d)
+    ctx = ctx_for(g)
+    ps = d['ps']
+    pmf = ctx.set_ps(ps, want_pmf=True)
+    np.testing.assert_allclose(pmf, d['pmf'], rtol=RTOL, atol=ATOL)
+    runs = d['perms'].shape[0]
+    ctx.run_fused(runs, n.PERM_HOST, d['perms'], n.FUSE_CANON)
+    per = ctx.canon_last_runs(runs)
+    ref = d['canon_per_run']
+    if not spanning:
+        assert np.all(per[:, :, 0] == 0)
+        per = per[:, :, 1:]
+    np.testing.assert_allclose(per, ref, rtol=RTOL, atol=ATOL)
+    # host rows -> bond_canonical_statistics (hpc.py:443-515)
+    rows = golden_rows(d)
+    for i in (0, len(ps) // 2, len(ps) - 1):
+        st = hpc.bond_canonical_statistics(rows[0].astype(np.dtype(hpc.microcanonical_statistics_dtype(spanning))),
+                                           d['pmf'][i])
+        o = 1 if spanning else 0
+        if spanning:
+            np.testing.assert_allclose(st['percolation_probability'][0], ref[0, i, 0], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(st['max_cluster_size'][0], ref[0, i, o], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(st['moments'][0], ref[0, i, o + 1:], rtol=RTOL, atol=ATOL)
+    # device reduction == functools.reduce(bond_reduce, ...) of the reference
+    count, mean, m2 = ctx.canon_export()
+    red = hpc._canonical_averages_from_partials(count, mean, m2, spanning)
+    ref_red = d['reduced'].view(np.dtype(hpc.canonical_averages_dtype(spanning)))
+    assert (red['number_of_runs'] == runs).all()
+    for f in red.dtype.names:
+        if f.endswith('_mean'):
+            np.testing.assert_allclose(red[f], ref_red[f], rtol=RTOL, atol=ATOL)
+        elif f.endswith('_m2'):
+            # M2 is a sum of squared differences: absolute accuracy scales with mean^2
+            scale = np.abs(ref_red[f.replace('_m2', '_mean')]).max() ** 2
+            np.testing.assert_allclose(red[f], ref_red[f], rtol=1e-9, atol=1e-13 * scale)
+    fin = hpc.finalize_canonical_averages(g.num_nodes, ps, red, float(d['alpha']))
+    ref_fin = d['finalized'].view(np.dtype(hpc.finalized_canonical_averages_dtype(spanning)))
+    for f in fin.dtype.names:
+        scale = np.nanmax(np.abs(ref_fin[f])) if np.isfinite(ref_fin[f]).any() else 0.0
+        np.testing.assert_allclose(fin[f], ref_fin[f], rtol=1e-8, atol=1e-12 * scale, equal_nan=True)
+    ctx.close()
+
+
+def test_binomial_pmf_drop_in():
+    import scipy.stats
+    from pypercolate_b200 import percolate
+    from oracle import oracle
+    # percolate/test/test_percolate.py:283-295
+    np.testing.assert_allclose(percolate._binomial_pmf(1000, 0.01).sum(), 1.0)
+    np.testing.assert_allclose(percolate._binomial_pmf(100, 0.1),
+                               scipy.stats.binom.pmf(np.arange(101), n=100, p=0.1))
+    for M, p in [(12, 0.0), (12, 1.0), (1984, 0.5), (130560, 0.45), (130560, 0.5), (130560, 0.999),
+                 (2095104, 0.5)]:
+        got = percolate._binomial_pmf(M, p)
+        np.testing.assert_allclose(got, oracle.binomial_pmf(M, p), rtol=1e-12, atol=0)
+
+
+# ---------------------------------------------------------------------------
+# the public Python API (drop-in behaviour)
+# ---------------------------------------------------------------------------
+def kat_graph(span):
+    import networkx as nx
+    ret = nx.Graph()
+    ret.add_nodes_from(range(9))
+    ret.add_edges_from([(i, i + j) for i in [1, 4, 7] for j in [-1, 1]])
+    ret.add_edges_from([(i, i + j) for i in [3, 4, 5] for j in [-3, 3]])
+    if span:
+        ret.add_nodes_from(range(9, 12), span=0)
+        ret.add_nodes_from(range(12, 15), span=1)
+        ret.add_edges_from([(0, 9), (3, 10), (6, 11)], span=0)
+        ret.add_edges_from([(2, 12), (5, 13), (8, 14)], span=1)
+    return ret
+
+
+@pytest.mark.parametrize("span", [True, False])
+def test_sample_states_known_answers(span):
+    # percolate/test/test_percolate.py:92-192
+    from pypercolate_b200 import percolate
+    from test_oracle import KAT_EDGES, KAT_MAX, KAT_MOMENTS, KAT_PERM, KAT_SPAN
+    it = percolate.sample_states(kat_graph(span), spanning_cluster=span)
+    first = next(it)
+    assert first['n'] == 0 and first['N'] == 9 and first['M'] == 12
+    assert first['max_cluster_size'] == 1 and np.array_equal(first['moments'], np.ones(5) * 8)
+    assert ('has_spanning_cluster' in first) == span and 'edge' not in first
+    np.random.seed(42)            # drawn only when advanced past n == 0
+    states = [first] + list(it)
+    assert [s['n'] for s in states] == list(range(13))
+    assert [s['max_cluster_size'] for s in states] == KAT_MAX
+    for s in states:
+        assert np.array_equal(s['moments'], KAT_MOMENTS[s['n']])
+        assert s['moments'].dtype == np.float64
+    assert [s['edge'] for s in states[1:]] == [KAT_EDGES[e] for e in KAT_PERM]
+    if span:
+        assert [s['has_spanning_cluster'] for s in states] == KAT_SPAN
+    # copy_result=False hands out one dict
+    np.random.seed(42)
+    it = percolate.sample_states(kat_graph(span), spanning_cluster=span, copy_result=False)
+    objs = {id(s) for s in it}
+    assert len(objs) == 1
+
+
+def test_bond_sample_states_and_statistics_api():
+    # percolate/test/test_hpc.py:250-334
+    from pypercolate_b200 import hpc, percolate
+    d = load_golden("hpc_grid3")
+    ref = golden_rows(d)
+    pg = percolate.percolation_graph(percolate.spanning_2d_grid(3))
+    for r, seed in enumerate(d['seeds'][:5]):
+        arr = hpc.bond_microcanonical_statistics(seed=int(seed), **pg)
+        assert arr.dtype == np.dtype(hpc.microcanonical_statistics_dtype(True))
+        assert_rows_equal(arr, ref[r].astype(arr.dtype))
+        gen = hpc.bond_sample_states(seed=int(seed), **pg)
+        objs = set()
+        for n, state in enumerate(gen):
+            objs.add(id(state))
+            assert state.shape == (1,) and state['n'][0] == n
+            if n:
+                assert state['edge'][0] == arr['edge'][n]
+            assert state['max_cluster_size'][0] == arr['max_cluster_size'][n]
+            assert np.array_equal(state['moments'][0], arr['moments'][n])
+        assert n == pg['num_edges'] and len(objs) == 1
+    # non-integer seeds go through RandomState on the host (hpc.py:195)
+    arr = hpc.bond_microcanonical_statistics(seed=[1, 2, 3], **pg)
+    perm = np.random.RandomState([1, 2, 3]).permutation(12)
+    assert np.array_equal(arr['edge'][1:], perm)
+    batch = hpc.bond_microcanonical_statistics_batch(seeds=d['seeds'].astype(np.uint32), **pg)
+    assert_rows_equal(batch, ref.astype(batch.dtype))
+
+
+@pytest.mark.parametrize("name", ORIG_FIXTURES)
+def test_original_api_matches_reference_golden(name):
+    """np.random.seed(s); statistics(...) draws the same bond orders as the
+    reference and must reproduce its microcanonical and canonical averages."""
+    from pypercolate_b200 import percolate
+    d = load_golden(name)
+    g = golden_graph(d)
+    spanning = bool(int(d['spanning']))
+    runs, alpha, seed = int(d['runs']), float(d['alpha']), int(d['seed'])
+    np.random.seed(seed)
+    it = percolate.microcanonical_averages(g, runs=runs, spanning_cluster=spanning, alpha=alpha)
+    micro = percolate.microcanonical_averages_arrays(it)
+    assert micro['N'] == g.num_nodes and micro['M'] == g.num_edges
+    keys = [k[6:] for k in d if k.startswith('micro_') and k not in ('micro_N', 'micro_M')]
+    assert sorted(keys) == sorted(k for k in micro if k not in ('N', 'M'))
+    for k in keys:
+        scale = np.abs(d['micro_' + k]).max()
+        np.testing.assert_allclose(micro[k], d['micro_' + k], rtol=RTOL, atol=1e-13 * scale, err_msg=k)
+    canon = percolate.canonical_averages(d['ps'], micro)
+    for k in (k[6:] for k in d if k.startswith('canon_')):
+        if k in ('N', 'M', 'ps'):
+            assert np.array_equal(canon[k], d['canon_' + k])
+            continue
+        scale = np.abs(d['canon_' + k]).max()
+        np.testing.assert_allclose(canon[k], d['canon_' + k], rtol=RTOL, atol=1e-13 * scale, err_msg=k)
+    # generator form: per-n dictionaries, n == 0 before any random draw
+    np.random.seed(seed)
+    dicts = list(percolate.microcanonical_averages(g, runs=runs, spanning_cluster=spanning, alpha=alpha))
+    assert [x['n'] for x in dicts] == list(range(g.num_edges + 1))
+    via = percolate.microcanonical_averages_arrays(iter(dicts))
+    for k in keys:
+        np.testing.assert_array_equal(via[k], micro[k])
+    # statistics() end to end
+    np.random.seed(seed)
+    stats = percolate.statistics(g, d['ps'], spanning_cluster=spanning, alpha=alpha, runs=runs)
+    for k in canon:
+        np.testing.assert_array_equal(stats[k], canon[k])
+    # sample_states of the first run
+    np.random.seed(seed)
+    states = list(percolate.sample_states(g, spanning_cluster=spanning))
+    assert [s['max_cluster_size'] for s in states] == d['states_max'].tolist()
+    np.testing.assert_allclose(np.stack([s['moments'] for s in states]), d['states_moments'], rtol=RTOL)
+    single = None
+    np.random.seed(seed)
+    single = percolate.single_run_arrays(graph=g, spanning_cluster=spanning)
+    np.testing.assert_array_equal(single['max_cluster_size'], d['states_max'])
+    assert single['moments'].shape == (5, g.num_edges + 1)
+    if spanning:
+        assert np.array_equal(single['has_spanning_cluster'], d['states_span'])
+
+
+def test_microcanonical_averages_initial_iteration():
+    # percolate/test/test_percolate.py:234-265
+    import scipy.stats
+    from pypercolate_b200 import percolate
+    for span in (True, False):
+        state = np.random.get_state()[1].copy()
+        ret = next(percolate.microcanonical_averages(kat_graph(span), spanning_cluster=span))
+        assert np.array_equal(np.random.get_state()[1], state)     # nothing drawn yet
+        assert ret['n'] == 0 and ret['max_cluster_size'] == 1.0
+        np.testing.assert_allclose(ret['max_cluster_size_ci'], np.ones(2))
+        np.testing.assert_allclose(ret['moments'], np.ones(5) * 8)
+        np.testing.assert_allclose(ret['moments_ci'], np.ones((5, 2)) * 8)
+        assert ('spanning_cluster' in ret) == span
+        if span:
+            assert ret['spanning_cluster'] == 1 / 42
+            np.testing.assert_allclose(
+                np.array([0, 1]) + np.array([1, -1]) *
+                scipy.stats.beta.cdf(ret['spanning_cluster_ci'], a=1, b=41),
+                scipy.stats.norm.cdf(-1) * np.ones(2))
+
+
+def test_fused_hpc_batch_equals_reference_map_reduce():
+    """bond_canonical_averages_batch == reduce(bond_reduce, map(bond_run, seeds))
+    (percolate/share/jugfile.py:57-135), checked against the reference's
+    per-run values from the golden file."""
+    from pypercolate_b200 import hpc, percolate
+    d = load_golden("hpc_grid8")
+    pg = percolate.percolation_graph(percolate.spanning_2d_grid(8))
+    got = hpc.bond_canonical_averages_batch(seeds=d['seeds'].astype(np.uint32), ps=d['ps'], **pg)
+    ref = d['reduced'].view(np.dtype(hpc.canonical_averages_dtype(True)))
+    for f in got.dtype.names:
+        scale = np.abs(ref[f.replace('_m2', '_mean')]).max() ** (2 if f.endswith('_m2') else 1)
+        np.testing.assert_allclose(got[f], ref[f], rtol=1e-9, atol=1e-13 * scale)
+
+
+# ---------------------------------------------------------------------------
+# full-size properties (BASELINE configs 3-5): no oracle can walk these in bulk
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,L,runs,check", [("2d", 256, 64, 2), ("2d", 1024, 4, 1), ("3d", 64, 6, 1)])
+def test_full_size_invariants(kind, L, runs, check):
+    from pypercolate_b200 import lowering
+    from oracle import oracle
+    n = _native()
+    g = (lowering.lowered_spanning_2d_grid if kind == "2d" else lowering.lowered_spanning_3d_grid)(L)
+    N, M = g.num_nodes, g.num_edges
+    ctx = ctx_for(g)
+    seeds = np.arange(runs, dtype=np.uint32) + 2024
+    mode = n.PERM_PHILOX
+    chunk = max(1, min(runs, (1 << 30) // ((M + 1) * 53)))
+    for r0 in range(0, runs, chunk):
+        rows, perms = ctx.run_rows(min(chunk, runs - r0), mode, seeds[r0:r0 + chunk], want_perms=True)
+        for r in range(rows.shape[0]):
+            x = rows[r]
+            assert np.array_equal(np.sort(perms[r]), np.arange(M))          # a permutation
+            assert np.array_equal(x['edge'][1:], perms[r].astype(np.uint32))
+            assert np.array_equal(x['n'], np.arange(M + 1, dtype=np.uint32))
+            mx = x['max_cluster_size'].astype(np.int64)
+            assert mx[0] == 1 and mx[-1] == N and np.all(np.diff(mx) >= 0)   # connected lattice
+            assert np.all(np.diff(x['has_spanning_cluster'].astype(np.int8)) >= 0)
+            assert x['has_spanning_cluster'][-1] and not x['has_spanning_cluster'][0]
+            mom = x['moments']
+            assert np.array_equal(mom[:, 1], (N - mx).astype(np.uint64))     # sum s = N
+            assert np.all(np.diff(mom[:, 0].astype(np.int64)) <= 0)          # cluster count
+            assert mom[0].tolist() == [N - 1] * 5 and mom[-1].tolist() == [0] * 5
+            assert np.all(mom[:, 0].astype(np.int64) + 1 + np.arange(M + 1) >= N)  # >= N - n clusters
+            if r0 + r < check:     # bit-exact against the oracle on the same bond order
+                ref = oracle.sweep_rows(N, M, g.eu, g.ev, g.side_mask, False, perms[r])
+                assert_rows_equal(x, ref, "%s L=%d" % (kind, L))
+    ctx.close()
+
+
+def test_statistical_agreement_of_philox_mode():
+    """Philox bond orders are validated statistically: the spanning probability
+    at the 2D threshold from 2000 Philox runs must sit inside the reference
+    stream's own 5-sigma binomial interval (and vice versa)."""
+    from pypercolate_b200 import lowering
+    n = _native()
+    g = lowering.lowered_spanning_2d_grid(32)
+    runs = 2000
+    res = {}
+    for mode in (n.PERM_MT19937, n.PERM_PHILOX):
+        ctx = ctx_for(g)
+        ctx.run_fused(runs, mode, np.arange(runs, dtype=np.uint32) + 1, n.FUSE_MICRO)
+        mean, var = ctx.micro_finalize()
+        res[mode] = (mean, var)
+        ctx.close()
+    for i in (g.num_edges // 2, int(0.45 * g.num_edges), int(0.55 * g.num_edges)):
+        k0, k1 = res[n.PERM_MT19937][0][0][i], res[n.PERM_PHILOX][0][0][i]
+        p = (k0 + k1) / (2 * runs)
+        sigma = np.sqrt(2 * runs * p * (1 - p)) + 1.0
+        assert abs(k0 - k1) < 5 * sigma
+        m0, m1 = res[n.PERM_MT19937][0][1][i], res[n.PERM_PHILOX][0][1][i]
+        s = np.sqrt((res[n.PERM_MT19937][1][0][i] + res[n.PERM_PHILOX][1][0][i]) / runs)
+        assert abs(m0 - m1) < 5 * s
+
+
+def test_missing_graph_and_bad_arguments_fail_loudly():
+    n = _native()
+    ctx = n.Context(0)
+    with pytest.raises(n.NativeError):
+        ctx.run_rows(1, n.PERM_HOST, np.zeros((1, 0), np.int32))
+    with pytest.raises(n.NativeError):
+        n.Context(10 ** 6)
+    from pypercolate_b200 import lowering
+    g = lowering.lowered_spanning_2d_grid(4)
+    ctx.set_graph(g)
+    with pytest.raises(n.NativeError):
+        ctx.run_fused(2, n.PERM_HOST, np.zeros((2, g.num_edges), np.int32), n.FUSE_CANON)  # no ps
+    with pytest.raises(n.NativeError):
+        ctx.micro_finalize()                                                                # no runs
+    with pytest.raises(n.NativeError):
+        ctx.set_ps(np.array([1.5]))
+    ctx.close()

@@ -1,0 +1,179 @@
+"""Host-side mirror of the reference interface (no GPU): dtypes, the
+(count, mean, M2) chain of percolate.hpc, lazy error behaviour."""
+import functools
+
+import networkx as nx
+import numpy as np
+import pytest
+import scipy.stats
+
+from conftest import HPC_FIXTURES, RTOL, load_golden
+from pypercolate_b200 import hpc, percolate
+import pypercolate_b200
+
+
+def test_public_surface_matches_reference_init():
+    # percolate/__init__.py:88-97
+    for name in ("sample_states", "single_run_arrays", "microcanonical_averages",
+                 "microcanonical_averages_arrays", "canonical_averages", "spanning_1d_chain",
+                 "spanning_2d_grid", "statistics"):
+        assert callable(getattr(pypercolate_b200, name))
+    assert pypercolate_b200.hpc is hpc and pypercolate_b200.percolate is percolate
+
+
+# -- dtypes (percolate/test/test_hpc.py:25-141) -----------------------------------
+@pytest.mark.parametrize("spanning", [True, False])
+def test_microcanonical_statistics_dtype(spanning):
+    dt = np.dtype(hpc.microcanonical_statistics_dtype(spanning))
+    assert dt.itemsize == (53 if spanning else 52)
+    assert dt['n'] == np.uint32 and dt['edge'] == np.uint32
+    assert dt['max_cluster_size'] == np.uint32
+    assert dt['moments'].shape == (5,) and dt['moments'].base == np.uint64
+    assert ('has_spanning_cluster' in dt.names) == spanning
+    assert dt.fields['moments'][1] == (13 if spanning else 12)
+
+
+@pytest.mark.parametrize("spanning", [True, False])
+def test_canonical_dtypes(spanning):
+    dt = np.dtype(hpc.canonical_statistics_dtype(spanning))
+    assert ('percolation_probability' in dt.names) == spanning
+    assert dt['moments'].shape == (5,) and dt['max_cluster_size'] == np.float64
+    dt = np.dtype(hpc.canonical_averages_dtype(spanning))
+    assert dt['number_of_runs'] == np.uint32
+    assert ('percolation_probability_mean' in dt.names) == spanning
+    assert dt['moments_mean'].shape == (5,) and dt['moments_m2'].shape == (5,)
+    dt = np.dtype(hpc.finalized_canonical_averages_dtype(spanning))
+    for f in ('p', 'alpha', 'percolation_strength_mean', 'percolation_strength_std'):
+        assert dt[f] == np.float64
+    assert dt['percolation_strength_ci'].shape == (2,)
+    assert dt['moments_ci'].shape == (5, 2)
+    assert ('percolation_probability_ci' in dt.names) == spanning
+
+
+# -- initialize / reduce / finalize against the reference's outputs -----------------
+def canon_stats_from_golden(d, r):
+    spanning = bool(int(d['spanning']))
+    c = d['canon_per_run'][r]
+    st = np.empty(c.shape[0], dtype=hpc.canonical_statistics_dtype(spanning))
+    o = 0
+    if spanning:
+        st['percolation_probability'] = c[:, 0]
+        o = 1
+    st['max_cluster_size'] = c[:, o]
+    st['moments'] = c[:, o + 1:]
+    return st
+
+
+@pytest.mark.parametrize("name", [n for n in HPC_FIXTURES if n not in
+                                  ("hpc_chain1", "hpc_preconnected")])
+def test_reduce_finalize_chain_matches_reference(name):
+    d = load_golden(name)
+    spanning = bool(int(d['spanning']))
+    runs = d['canon_per_run'].shape[0]
+    parts = [hpc.bond_initialize_canonical_averages(canon_stats_from_golden(d, r))
+             for r in range(runs)]
+    assert all((p['number_of_runs'] == 1).all() for p in parts)
+    red = functools.reduce(hpc.bond_reduce, parts)
+    ref_red = d['reduced'].view(np.dtype(hpc.canonical_averages_dtype(spanning)))
+    assert (red['number_of_runs'] == runs).all()
+    for f in red.dtype.names:
+        np.testing.assert_allclose(red[f], ref_red[f], rtol=RTOL, atol=1e-12 * np.abs(ref_red[f]).max())
+    fin = hpc.finalize_canonical_averages(int(d['N']), d['ps'], red, float(d['alpha']))
+    ref_fin = d['finalized'].view(np.dtype(hpc.finalized_canonical_averages_dtype(spanning)))
+    for f in fin.dtype.names:
+        scale = np.nanmax(np.abs(ref_fin[f])) if np.isfinite(ref_fin[f]).any() else 0.0
+        np.testing.assert_allclose(fin[f], ref_fin[f], rtol=1e-9, atol=1e-12 * scale,
+                                   equal_nan=True, err_msg=f)
+
+
+def test_bond_reduce_is_associative_and_matches_numpy():
+    # percolate/test/test_hpc.py:454-524
+    rng = np.random.RandomState(5)
+    nump, runs = 6, 17
+    stats = []
+    for _ in range(runs):
+        s = np.empty(nump, dtype=hpc.canonical_statistics_dtype(True))
+        s['percolation_probability'] = rng.rand(nump)
+        s['max_cluster_size'] = rng.rand(nump) * 100
+        s['moments'] = rng.rand(nump, 5) * 1e6
+        stats.append(s)
+    parts = [hpc.bond_initialize_canonical_averages(s) for s in stats]
+    left = functools.reduce(hpc.bond_reduce, parts)
+    right = functools.reduce(lambda a, b: hpc.bond_reduce(b, a), parts)
+    tree = hpc.bond_reduce(functools.reduce(hpc.bond_reduce, parts[:8]),
+                           functools.reduce(hpc.bond_reduce, parts[8:]))
+    for key in ('percolation_probability', 'max_cluster_size', 'moments'):
+        x = np.stack([s[key] for s in stats])
+        for red in (left, right, tree):
+            np.testing.assert_allclose(red[key + '_mean'], x.mean(axis=0), rtol=1e-7)
+            np.testing.assert_allclose(red[key + '_m2'], ((x - x.mean(axis=0)) ** 2).sum(axis=0),
+                                       rtol=1e-7, atol=1e-6)
+    assert (left['number_of_runs'] == runs).all()
+
+
+def test_finalize_formulas():
+    # percolate/test/test_hpc.py:527-694
+    nump, runs, N, alpha = 4, 9, 50, 0.1
+    avg = np.zeros(nump, dtype=hpc.canonical_averages_dtype(True))
+    rng = np.random.RandomState(3)
+    avg['number_of_runs'] = runs
+    for key in ('percolation_probability', 'max_cluster_size', 'moments'):
+        avg[key + '_mean'] = rng.rand(*avg[key + '_mean'].shape) * 10
+        avg[key + '_m2'] = rng.rand(*avg[key + '_m2'].shape) * 5
+    ps = np.linspace(0.1, 0.9, nump)
+    fin = hpc.finalize_canonical_averages(N, ps, avg, alpha)
+    assert (fin['p'] == ps).all() and (fin['alpha'] == alpha).all()
+    np.testing.assert_allclose(fin['percolation_probability_mean'], avg['percolation_probability_mean'])
+    np.testing.assert_allclose(fin['percolation_strength_mean'], avg['max_cluster_size_mean'] / N)
+    np.testing.assert_allclose(fin['moments_std'], np.sqrt(avg['moments_m2'] / (runs - 1)) / N)
+    lo, hi = fin['percolation_strength_ci'][:, 0], fin['percolation_strength_ci'][:, 1]
+    scale = fin['percolation_strength_std'] / np.sqrt(runs)
+    cdf = scipy.stats.t.cdf((hi - fin['percolation_strength_mean']) / scale, df=runs - 1)
+    np.testing.assert_allclose(cdf, 1 - alpha / 2, rtol=1e-6)
+    np.testing.assert_allclose(hi - fin['percolation_strength_mean'],
+                               fin['percolation_strength_mean'] - lo, rtol=1e-9)
+
+
+# -- lazy error behaviour (percolate/test/test_percolate.py:76-89, 206-231) ---------
+def test_sample_states_errors_surface_on_first_next():
+    it = percolate.sample_states(nx.Graph(), model='site')
+    with pytest.raises(ValueError):
+        next(it)
+    it = percolate.sample_states(nx.Graph())
+    with pytest.raises(ValueError):
+        next(it)
+    g = nx.path_graph(4)
+    g.nodes[0]['span'] = 0
+    it = percolate.sample_states(g)
+    with pytest.raises(ValueError):
+        next(it)
+
+
+@pytest.mark.parametrize("kwargs", [dict(runs=0), dict(runs=-3), dict(runs='x'), dict(alpha=0.0),
+                                    dict(alpha=1.0), dict(alpha='x'), dict(alpha=-0.5)])
+def test_microcanonical_averages_argument_errors(kwargs):
+    it = percolate.microcanonical_averages(percolate.spanning_2d_grid(3), **kwargs)
+    with pytest.raises(ValueError):
+        next(it)
+
+
+def test_bond_sample_states_needs_two_sides():
+    g = nx.path_graph(3)
+    it = hpc.bond_sample_states(g, 3, 2, seed=1, spanning_cluster=True,
+                                auxiliary_node_attributes={}, auxiliary_edge_attributes={},
+                                spanning_sides=[0])
+    with pytest.raises(ValueError):
+        next(it)
+
+
+def test_alpha_1sigma():
+    assert percolate.alpha_1sigma == 2 * scipy.stats.norm.cdf(-1.0)
+
+
+def test_spanning_graph_builders():
+    g = percolate.spanning_2d_grid(3)
+    assert g.number_of_nodes() == 15
+    assert sum(1 for _, a in g.nodes(data=True) if 'span' in a) == 6
+    assert sum(1 for *_, a in g.edges(data=True) if 'span' in a) == 6
+    c = percolate.spanning_1d_chain(4)
+    assert c.number_of_nodes() == 6 and c.nodes[0]['span'] == 0 and c.nodes[5]['span'] == 1
