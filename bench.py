@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""
+Headline benchmark: bond-additions/s of the fused Newman-Ziff hot path on the
+L = 256 square lattice (BASELINE.json config 3: 1e5 runs, fused microcanonical
++ canonical averaging at 100 p values, runs sharded over the GPUs of one box).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm
+    python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm
+
+A step is one pass of the hot path over the whole batch of runs: bond orders
+(Philox, on the device) -> union-find sweep -> per-n exact sums over runs and
+per-run binomial contraction -> (multi-GPU) one NCCL exchange -> per-n mean /
+variance.  Strong scaling: the 1e5 runs are split over the ranks.
+
+One JSON line is printed by rank 0 (see the driver contract in the task text).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+L = 256
+TOTAL_RUNS = int(os.environ.get("PZ_BENCH_RUNS", "100000"))
+NUM_P = 100
+METRIC = "bond-additions/sec (L=256 square lattice, fused microcanonical + canonical averaging)"
+UNIT = "bond-additions/s"
+# algorithmic bytes per bond addition of the fused 2D path:
+# 4 (bond order) + 8 (endpoints) + 8 (two root look-ups) + 8 * (N-1)/M (merge writes)
+ALGO_BYTES_PER_BOND = 20.0 + 8.0 * (L * L - 1) / (2 * L * (L - 1))
+
+
+def workload_config(n_gpus, runs_total):
+    return {
+        "workload": "spanning_2d_grid L=256 (N=65536, M=130560), %d runs total, Philox bond orders "
+                    "on device, fused microcanonical sums + per-run canonical contraction at "
+                    "%d p in [0.45, 0.55]" % (runs_total, NUM_P),
+        "runs_total": runs_total,
+        "runs_per_gpu": runs_total // n_gpus,
+        "num_p": NUM_P,
+        "parallelism": "runs sharded over %d GPU(s), one NCCL exchange per step" % n_gpus,
+        "l2_policy": "inputs larger than L2 (bond orders + merge records of a launch: several GB)",
+    }
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(smax))
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def cpu_port_rate(seconds_target, threads=None):
+    """The oracle port (oracle/pz_oracle.c: reference semantics, rows
+    materialised, numpy-stream permutation inside) on the host cores."""
+    from oracle import oracle
+    from pypercolate_b200 import lowering
+    g = lowering.lowered_spanning_2d_grid(L)
+    cores = threads or os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    warm = np.arange(cores, dtype=np.uint32) + 1
+    t0 = time.perf_counter()
+    oracle.sweep_many_checksums(g.num_nodes, g.num_edges, g.eu, g.ev, g.side_mask, False, warm)
+    per_wave = max(time.perf_counter() - t0, 1e-3)
+    waves = max(1, int(seconds_target / per_wave))
+    seeds = np.arange(cores * waves, dtype=np.uint32) + 1000
+    t0 = time.perf_counter()
+    oracle.sweep_many_checksums(g.num_nodes, g.num_edges, g.eu, g.ev, g.side_mask, False, seeds)
+    dt = time.perf_counter() - t0
+    return seeds.size * g.num_edges / dt, cores, seeds.size, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    vals = []
+    per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    cores = runs = 0
+    for i in range(args.warmup + args.steps):
+        rate, cores, runs, dt = cpu_port_rate(per_step)
+        if i >= args.warmup:
+            vals.append((rate, dt))
+    value = float(np.mean([v for v, _ in vals]))
+    sample = ("%d runs of L=256 per step (permutation via the numpy MT19937 stream + sweep + "
+              "53-byte rows), OpenMP over %d threads" % (runs, cores))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": float(np.mean([d for _, d in vals]) * 1e3), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(args.gpus, TOTAL_RUNS),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference is pure Python (~4e4 bond-additions/s per core, BASELINE.md) and "
+                "cannot travel to the GPU box; this arm times the C restatement of its algorithm "
+                "(oracle/pz_oracle.c) on all host cores",
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--runs", type=int, default=TOTAL_RUNS, help="total runs per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__
+    __graft_entry__.build()
+    from pypercolate_b200 import _native, hpc, lowering, multi
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world,
+                                device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    g = lowering.lowered_spanning_2d_grid(L)
+    M, N = g.num_edges, g.num_nodes
+    ctx = _native.context_for(g, local)
+    ps = np.linspace(0.45, 0.55, NUM_P)
+    ctx.set_ps(ps)
+    lo, hi = multi.shard_bounds(args.runs, rank, world)
+    my_runs = hi - lo
+    seeds_host = (np.arange(lo, hi, dtype=np.uint64) * 2654435761 % (2 ** 32)).astype(np.uint32)
+    seeds_dev = torch.from_numpy(seeds_host.view(np.int32)).cuda()
+    flags = _native.FUSE_MICRO | _native.FUSE_CANON
+    mode = _native.PERM_PHILOX | _native.SEEDS_ON_DEVICE
+
+    def step_device():
+        """inputs (graph, seeds, binomial weights) resident in HBM"""
+        ctx.reset_accumulators()
+        ctx.run_fused(my_runs, mode, seeds_dev.data_ptr(), flags)
+        if world > 1:
+            multi.allreduce_context(ctx)
+        ctx.micro_finalize_device_only()
+
+    def step_e2e():
+        """the public call: host seeds / ps in, host statistics out"""
+        return hpc.bond_statistics_batch(g, N, M, seeds_host, ps, 0.3173, device=local,
+                                         rng='philox', distributed=world > 1)
+
+    # ---- device-resident throughput -------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ctx.profile(True)
+    launches0 = ctx.launch_count
+    ctx.timer_start()
+    for _ in range(args.steps):
+        step_device()
+    ms = ctx.timer_stop()
+    barrier()
+    launches = ctx.launch_count - launches0
+    phases = ctx.profile_read()
+    ctx.profile(False)
+    clocks = sampler.stop() if sampler else None
+
+    # ---- end to end through the public API ---------------------------------------
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    t = torch.tensor([ms, e2e_s * 1e3, float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, e2e_ms, launches = float(tmax[0]), float(tmax[1]), int(tsum[2])
+    else:
+        e2e_ms = e2e_s * 1e3
+
+    if rank == 0:
+        bonds_per_step = float(args.runs) * M
+        value = bonds_per_step * args.steps / (ms * 1e-3)
+        e2e_value = bonds_per_step * args.steps / (e2e_ms * 1e-3)
+        sweep_ms, sweep_launches = phases["sweep"]
+        peak, peak_src = measured_peak()
+        bonds_per_launch = float(my_runs) * M * args.steps / max(1, sweep_launches)
+        achieved = ALGO_BYTES_PER_BOND * bonds_per_launch / (sweep_ms / max(1, sweep_launches) * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "sweep_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                tj = json.load(open(tpath))
+                traffic = float(tj["dram_bytes_per_bond"]) * bonds_per_launch
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": workload_config(world, args.runs),
+            "runs_per_s": float(args.runs) * args.steps / (ms * 1e-3),
+            "roofline": {
+                "bound": "hbm", "kernel": "sweep_kernel (union-find, shared-memory latency bound)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_bond": ALGO_BYTES_PER_BOND,
+                "avg_launch_ms": sweep_ms / max(1, sweep_launches),
+                "bonds_per_launch": bonds_per_launch,
+            },
+            "phase_ms_per_step_rank0": {k: v[0] / args.steps for k, v in phases.items() if v[1]},
+            "e2e": {
+                "value": e2e_value, "unit": UNIT,
+                "h2d_bytes_per_step": int(seeds_host.nbytes + ps.nbytes),
+                "d2h_bytes_per_step": int(13 * (M + 1) * 8 + 2 * NUM_P * 7 * 8),
+                "ms_per_step": e2e_ms / args.steps,
+                "api": "pypercolate_b200.hpc.bond_statistics_batch (host seeds/ps in, "
+                       "microcanonical arrays + finalized canonical averages out)",
+            },
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            rate, cores, nruns, dt = cpu_port_rate(12.0)
+            line["cpu_baseline"] = {
+                "value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": "%d runs of L=256 in %.1f s (numpy-stream permutation + sweep + rows), "
+                          "OpenMP over %d threads" % (nruns, dt, cores),
+            }
+        # sanity of the last e2e result (not timed)
+        assert res["number_of_runs"] == args.runs
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

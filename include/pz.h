@@ -42,6 +42,9 @@ enum pz_perm_mode {
     PZ_PERM_PHILOX = 3     /* uint32 seeds[R]; Philox4x32-10 bucketed Fisher-Yates       */
 };
 
+/* OR into a device-RNG perm_mode when the seeds already live in device memory */
+#define PZ_SEEDS_ON_DEVICE 0x100
+
 /* number of 64-bit words per bond count n in the micro accumulators */
 #define PZ_ACC_WORDS 25
 /* columns of a per-run canonical statistics row: P_span, max, moments[5] */
@@ -139,6 +142,7 @@ int pz_micro_import(pz_ctx *ctx, const uint64_t *src, int is_device, int64_t run
  *   mean_out  host double[7][M+1]: spanning count k, max, moments[0..4]
  *   var_out   host double[6][M+1]: unbiased variance (ddof=1) of max, moments[0..4];
  *             exactly 0.0 when all runs agree
+ * Both NULL: the arrays are computed and left on the device.
  */
 int pz_micro_finalize(pz_ctx *ctx, double *mean_out, double *var_out);
 
@@ -199,6 +203,10 @@ int pz_canon_last_runs(pz_ctx *ctx, double *out);
 #define PZ_PHASE_CKPT 6     /* run-state checkpoints (block scan)    */
 int pz_profile(pz_ctx *ctx, int enable);
 int pz_profile_read(pz_ctx *ctx, double *ms_out, int64_t *launches_out);
+
+/* device-side stopwatch: CUDA events recorded on the context's stream */
+int pz_timer_start(pz_ctx *ctx);
+int pz_timer_stop(pz_ctx *ctx, double *ms_out);
 
 /* number of kernels this context has launched since creation */
 int64_t pz_launch_count(const pz_ctx *ctx);

@@ -19,6 +19,7 @@ LIB_PATH = os.path.join(_HERE, "libpz_b200.so")
 
 PERM_HOST, PERM_DEVICE, PERM_MT19937, PERM_PHILOX = 0, 1, 2, 3
 FUSE_MICRO, FUSE_CANON = 1, 2
+SEEDS_ON_DEVICE = 0x100
 ACC_WORDS = 25
 CANON_COLS = 7
 
@@ -30,7 +31,7 @@ SYMBOLS = [
     "pz_micro_export", "pz_micro_import", "pz_micro_finalize", "pz_set_ps",
     "pz_convolve", "pz_canonical_statistics_rows", "pz_canon_export",
     "pz_canon_merge", "pz_canon_last_runs", "pz_launch_count",
-    "pz_make_perms", "pz_profile", "pz_profile_read", "pz_canon_reset",
+    "pz_make_perms", "pz_profile", "pz_profile_read", "pz_canon_reset", "pz_timer_start", "pz_timer_stop",
 ]
 
 
@@ -88,6 +89,8 @@ def load():
         L.pz_canon_merge.argtypes = [vp, i64, vp, vp]
         L.pz_canon_last_runs.argtypes = [vp, vp]
         L.pz_canon_reset.argtypes = [vp]
+        L.pz_timer_start.argtypes = [vp]
+        L.pz_timer_stop.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
         L.pz_launch_count.argtypes = [vp]
         L.pz_launch_count.restype = i64
         _lib = L
@@ -161,7 +164,7 @@ class Context(object):
             if a.shape != (R, self.M):
                 raise ValueError("perms must have shape (runs, num_edges)")
             return a, _ptr(a)
-        if perm_mode == PERM_DEVICE:
+        if perm_mode == PERM_DEVICE or (perm_mode & SEEDS_ON_DEVICE):
             return None, ctypes.c_void_p(int(src))
         a = np.ascontiguousarray(src, dtype=np.uint32)
         if a.shape != (R,):
@@ -222,6 +225,9 @@ class Context(object):
         var = np.empty((6, self.M + 1), dtype=np.float64)
         _check(self._L.pz_micro_finalize(self._h, _ptr(mean), _ptr(var)))
         return mean, var
+
+    def micro_finalize_device_only(self):
+        _check(self._L.pz_micro_finalize(self._h, None, None))
 
     # -- canonical ------------------------------------------------------------
     def set_ps(self, ps, want_pmf=False, M=None):
@@ -285,6 +291,14 @@ class Context(object):
         out = np.empty((R, self.num_p, CANON_COLS), dtype=np.float64)
         _check(self._L.pz_canon_last_runs(self._h, _ptr(out)))
         return out
+
+    def timer_start(self):
+        _check(self._L.pz_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = ctypes.c_double()
+        _check(self._L.pz_timer_stop(self._h, ctypes.byref(ms)))
+        return float(ms.value)
 
     @property
     def launch_count(self):

@@ -94,6 +94,8 @@ struct pz_ctx {
 
     int64_t launches = 0;
 
+    cudaEvent_t timer_a = nullptr, timer_b = nullptr;
+
     // optional per-phase device timing (CUDA events on this context's stream)
     bool profiling = false;
     double phase_ms[PZ_PHASES] = {0};
@@ -274,10 +276,12 @@ struct Chunk {
     const int32_t *perms_dev;
 };
 
-static int sweep_chunk(pz_ctx *c, int32_t R, int perm_mode, const void *perm_src, size_t run0,
+static int sweep_chunk(pz_ctx *c, int32_t R, int perm_mode_in, const void *perm_src, size_t run0,
                        Chunk *out)
 {
     const int32_t M = c->M;
+    const bool seeds_on_device = (perm_mode_in & PZ_SEEDS_ON_DEVICE) != 0;
+    const int perm_mode = perm_mode_in & ~PZ_SEEDS_ON_DEVICE;
     const int32_t *perms_dev = nullptr;
     const size_t pm = (size_t)R * (size_t)std::max(M, 1);
     if (perm_mode == PZ_PERM_DEVICE) {
@@ -290,15 +294,19 @@ static int sweep_chunk(pz_ctx *c, int32_t R, int perm_mode, const void *perm_src
                 PZ_CUDA(cudaMemcpyAsync(c->perms.p, (const int32_t *)perm_src + run0 * (size_t)M,
                                         (size_t)R * M * 4, cudaMemcpyHostToDevice, c->stream));
         } else {
-            PZ_CUDA(c->seeds.ensure((size_t)R));
-            PZ_CUDA(cudaMemcpyAsync(c->seeds.p, (const uint32_t *)perm_src + run0, (size_t)R * 4,
-                                    cudaMemcpyHostToDevice, c->stream));
+            const uint32_t *seeds_dev = (const uint32_t *)perm_src + run0;
+            if (!seeds_on_device) {
+                PZ_CUDA(c->seeds.ensure((size_t)R));
+                PZ_CUDA(cudaMemcpyAsync(c->seeds.p, (const uint32_t *)perm_src + run0, (size_t)R * 4,
+                                        cudaMemcpyHostToDevice, c->stream));
+                seeds_dev = c->seeds.p;
+            }
             int l = 0;
             PhaseTimer t(c, PZ_PHASE_PERM);
             if (perm_mode == PZ_PERM_PHILOX)
-                PZ_CUDA(launch_perm_philox(M, R, c->seeds.p, c->perms.p, c->stream, &l));
+                PZ_CUDA(launch_perm_philox(M, R, seeds_dev, c->perms.p, c->stream, &l));
             else
-                PZ_CUDA(launch_perm_mt19937(M, R, c->seeds.p, c->perms.p, c->stream, &l));
+                PZ_CUDA(launch_perm_mt19937(M, R, seeds_dev, c->perms.p, c->stream, &l));
             c->launches += l;
         }
     }
@@ -338,8 +346,11 @@ static int check_run_args(pz_ctx *c, int32_t R, int perm_mode, const void *perm_
     if (!c) return fail(PZ_ERR_ARG, "null context");
     if (c->N == 0) return fail(PZ_ERR_STATE, "no graph set (call pz_set_graph first)");
     if (R < 0) return fail(PZ_ERR_ARG, "R must be >= 0");
-    if (perm_mode < PZ_PERM_HOST || perm_mode > PZ_PERM_PHILOX)
+    const int base_mode = perm_mode & ~PZ_SEEDS_ON_DEVICE;
+    if (base_mode < PZ_PERM_HOST || base_mode > PZ_PERM_PHILOX)
         return fail(PZ_ERR_ARG, "unknown perm_mode");
+    if ((perm_mode & PZ_SEEDS_ON_DEVICE) && base_mode < PZ_PERM_MT19937)
+        return fail(PZ_ERR_ARG, "PZ_SEEDS_ON_DEVICE needs a device RNG mode");
     if (R > 0 && !perm_src && c->M > 0) return fail(PZ_ERR_ARG, "perm_src is NULL");
     return PZ_OK;
 }
@@ -552,7 +563,7 @@ int pz_micro_import(pz_ctx *c, const uint64_t *src, int is_device, int64_t runs)
 
 int pz_micro_finalize(pz_ctx *c, double *mean_out, double *var_out)
 {
-    if (!c || !mean_out || !var_out) return fail(PZ_ERR_ARG, "pz_micro_finalize: bad arguments");
+    if (!c || (!mean_out) != (!var_out)) return fail(PZ_ERR_ARG, "pz_micro_finalize: bad arguments");
     if (c->N == 0) return fail(PZ_ERR_STATE, "no graph set");
     if (c->micro_runs <= 0 || !c->acc.p) return fail(PZ_ERR_STATE, "pz_micro_finalize: no runs accumulated");
     PZ_CUDA(cudaSetDevice(c->device));
@@ -562,8 +573,10 @@ int pz_micro_finalize(pz_ctx *c, double *mean_out, double *var_out)
     PZ_CUDA(launch_micro_finalize(c->N, c->M, c->micro_runs, c->acc.p, c->span_cum.p, c->fin.p,
                                   c->fin.p + 7 * S, c->stream));
     c->launches += 2;
-    PZ_CUDA(cudaMemcpyAsync(mean_out, c->fin.p, 7 * S * 8, cudaMemcpyDeviceToHost, c->stream));
-    PZ_CUDA(cudaMemcpyAsync(var_out, c->fin.p + 7 * S, 6 * S * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (mean_out) {
+        PZ_CUDA(cudaMemcpyAsync(mean_out, c->fin.p, 7 * S * 8, cudaMemcpyDeviceToHost, c->stream));
+        PZ_CUDA(cudaMemcpyAsync(var_out, c->fin.p + 7 * S, 6 * S * 8, cudaMemcpyDeviceToHost, c->stream));
+    }
     PZ_CUDA(cudaStreamSynchronize(c->stream));
     return PZ_OK;
 }
@@ -705,6 +718,32 @@ int pz_profile_read(pz_ctx *c, double *ms_out, int64_t *launches_out)
 {
     if (!c || !ms_out || !launches_out) return fail(PZ_ERR_ARG, "pz_profile_read: bad arguments");
     for (int i = 0; i < PZ_PHASES; ++i) { ms_out[i] = c->phase_ms[i]; launches_out[i] = c->phase_launches[i]; }
+    return PZ_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+int pz_timer_start(pz_ctx *c)
+{
+    if (!c) return fail(PZ_ERR_ARG, "null context");
+    PZ_CUDA(cudaSetDevice(c->device));
+    if (!c->timer_a) { PZ_CUDA(cudaEventCreate(&c->timer_a)); PZ_CUDA(cudaEventCreate(&c->timer_b)); }
+    PZ_CUDA(cudaEventRecord(c->timer_a, c->stream));
+    return PZ_OK;
+}
+
+int pz_timer_stop(pz_ctx *c, double *ms_out)
+{
+    if (!c || !ms_out) return fail(PZ_ERR_ARG, "pz_timer_stop: bad arguments");
+    if (!c->timer_a) return fail(PZ_ERR_STATE, "pz_timer_stop: timer not started");
+    PZ_CUDA(cudaSetDevice(c->device));
+    PZ_CUDA(cudaEventRecord(c->timer_b, c->stream));
+    PZ_CUDA(cudaEventSynchronize(c->timer_b));
+    float ms = 0.f;
+    PZ_CUDA(cudaEventElapsedTime(&ms, c->timer_a, c->timer_b));
+    *ms_out = ms;
     return PZ_OK;
 }
 

@@ -301,24 +301,31 @@ cudaError_t launch_canon_runs(const StatsArgs &a, int32_t P, const double *pmf,
 }
 
 // ---------------------------------------------------------------------------
-// canon_reduce: (mean, M2) over the R runs of a batch for each of P*7 columns
-// (two-pass, fixed association -> deterministic)
+// canon_reduce: (mean, M2) over the R runs of a batch for each of P*7 columns.
+// Shifted-data form with the first run as pivot: d = x - x0,
+// mean = x0 + sum(d)/R, M2 = sum(d^2) - sum(d)^2/R.  Fixed association ->
+// deterministic; identical runs give M2 == 0 exactly, as the reference's
+// pairwise merges do (percolate/hpc.py:677-684).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) canon_reduce_kernel(int32_t R, int32_t cols, const double *runs,
                                                             double *mean, double *m2)
 {
     __shared__ double sh[8];
     const int c = blockIdx.x;
-    double part = 0.0;
-    for (int r = threadIdx.x; r < R; r += blockDim.x) part += runs[(size_t)r * cols + c];
-    const double mu = block_sum(part, sh) / (double)R;
-    part = 0.0;
+    const double x0 = runs[c];
+    double p1 = 0.0, p2 = 0.0;
     for (int r = threadIdx.x; r < R; r += blockDim.x) {
-        const double d = runs[(size_t)r * cols + c] - mu;
-        part += d * d;
+        const double d = runs[(size_t)r * cols + c] - x0;
+        p1 += d;
+        p2 += d * d;
     }
-    const double s2 = block_sum(part, sh);
-    if (threadIdx.x == 0) { mean[c] = mu; m2[c] = s2; }
+    const double s1 = block_sum(p1, sh);
+    const double s2 = block_sum(p2, sh);
+    if (threadIdx.x == 0) {
+        mean[c] = x0 + s1 / (double)R;
+        const double v = s2 - s1 * s1 / (double)R;
+        m2[c] = v > 0.0 ? v : 0.0;
+    }
 }
 
 cudaError_t launch_canon_reduce(int32_t R, int32_t cols, const double *runs, double *mean,

@@ -515,3 +515,75 @@ def bond_canonical_averages_batch(
                   seeds, _native.FUSE_CANON)
     count, mean, m2 = ctx.canon_export()
     return _canonical_averages_from_partials(count, mean, m2, spanning_cluster)
+
+
+def bond_statistics_batch(
+    perc_graph, num_nodes, num_edges, seeds, ps, alpha,
+    spanning_cluster=True, auxiliary_node_attributes=None,
+    auxiliary_edge_attributes=None, spanning_sides=None, **kwargs
+):
+    """One fused device pass over many runs: microcanonical AND canonical
+    averaging (BASELINE config 3).
+
+    Every run (one seed each) is swept once on the GPU; its per-bond statistics
+    are folded into (a) exact per-n sums over runs, from which the per-n means
+    and confidence intervals of ``microcanonical_averages_arrays``
+    (percolate/percolate.py:450-705, 968-1064) follow, and (b) per-run
+    canonical values for every ``p`` reduced to ``(count, mean, M2)`` and
+    finalised like ``finalize_canonical_averages`` (percolate/hpc.py:443-834).
+    With ``torch.distributed`` initialised (one process per GPU) the seeds are
+    the rank's shard and the partial results are combined with one NCCL
+    exchange (``pypercolate_b200.multi``).
+
+    Returns a dict with ``'microcanonical_averages_arrays'`` (same keys and
+    normalisation as the reference's), ``'canonical_averages'``
+    (``canonical_averages_dtype``), ``'finalized_canonical_averages'``
+    (``finalized_canonical_averages_dtype``) and ``'number_of_runs'``.
+
+    Backend keyword arguments: ``rng`` (``'philox'`` default, or ``'mt19937'``
+    for numpy's stream bit for bit), ``device``, ``distributed`` (combine
+    across ranks; default: whether ``torch.distributed`` is initialised).
+    """
+    from . import percolate as _percolate
+    lowered = _lower(perc_graph, spanning_cluster, auxiliary_node_attributes,
+                     auxiliary_edge_attributes, spanning_sides)
+    device = kwargs.get('device')
+    ctx = _native.context_for(lowered, _default_device() if device is None else device)
+    rng = kwargs.get('rng', 'philox')
+    mode = _native.PERM_PHILOX if rng == 'philox' else _native.PERM_MT19937
+    seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+    ps = np.ascontiguousarray(ps, dtype=np.float64)
+
+    ctx.set_ps(ps)
+    ctx.reset_accumulators()
+    ctx.run_fused(seeds.size, mode, seeds, _native.FUSE_MICRO | _native.FUSE_CANON)
+
+    distributed = kwargs.get('distributed')
+    if distributed is None:
+        try:
+            import torch.distributed as dist
+            distributed = dist.is_available() and dist.is_initialized()
+        except ImportError:
+            distributed = False
+    if distributed:
+        from . import multi
+        multi.allreduce_context(ctx)
+
+    runs = ctx.micro_runs
+    mean, var = ctx.micro_finalize()
+    arrays = _percolate._arrays_from_device(mean, var, runs, alpha, lowered.num_nodes,
+                                            lowered.num_edges, spanning_cluster)
+    for key in arrays:
+        if len(key) <= 1 or 'spanning_cluster' in key:
+            continue
+        arrays[key] = arrays[key] / lowered.num_nodes
+    count, cmean, cm2 = ctx.canon_export()
+    averages = _canonical_averages_from_partials(count, cmean, cm2, spanning_cluster)
+    finalized = finalize_canonical_averages(lowered.num_nodes, ps, averages, alpha)
+    ctx.reset_accumulators()
+    return {
+        'microcanonical_averages_arrays': arrays,
+        'canonical_averages': averages,
+        'finalized_canonical_averages': finalized,
+        'number_of_runs': runs,
+    }
