@@ -50,6 +50,7 @@ struct pz_ctx {
     int sms = 0;
     size_t smem_optin = 0;
     int force_kind = -1;
+    int team = 1;             // finder/merger team kernel (PZ_SWEEP_TEAM=0: single-warp kernel)
     size_t chunk_bytes = (size_t)8 << 30;
 
     // graph
@@ -180,6 +181,7 @@ int pz_create(int device, pz_ctx **out)
     c->smem_optin = prop.sharedMemPerBlockOptin;
     PZ_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     if (const char *e = getenv("PZ_FORCE_STORE")) c->force_kind = atoi(e);
+    if (const char *e = getenv("PZ_SWEEP_TEAM")) c->team = atoi(e);
     if (const char *e = getenv("PZ_CHUNK_BYTES")) c->chunk_bytes = (size_t)atoll(e);
     *out = c;
     return PZ_OK;
@@ -310,7 +312,7 @@ static int sweep_chunk(pz_ctx *c, int32_t R, int perm_mode_in, const void *perm_
             c->launches += l;
         }
     }
-    SweepPlan plan = plan_sweep(c->N, R, c->sms, c->smem_optin, c->force_kind);
+    SweepPlan plan = plan_sweep(c->N, R, c->sms, c->smem_optin, c->force_kind, c->team);
     if (plan.kind != STORE_G32 && c->N > 65536)
         return fail(PZ_ERR_ARG, "forced shared-memory store needs N <= 65536");
     const bool rec64 = plan.kind == STORE_G32;

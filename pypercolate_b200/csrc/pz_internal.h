@@ -32,11 +32,13 @@ struct SweepPlan {
     size_t slice_bytes;       // per warp
     int claim_log2;
     size_t gscratch_bytes;
+    int team;                 // 1: finder/merger team kernel (one CTA of 4 warps per run)
+    size_t store_bytes;       // team kernel: bytes of the parent store inside the CTA's smem
 };
 
 // choose store, CTA shape and grid for a graph of N nodes on a device with
 // `sms` SMs and `smem_optin` bytes of opt-in shared memory per CTA
-SweepPlan plan_sweep(int32_t N, int32_t R, int sms, size_t smem_optin, int force_kind);
+SweepPlan plan_sweep(int32_t N, int32_t R, int sms, size_t smem_optin, int force_kind, int team);
 cudaError_t launch_sweep(const SweepPlan &plan, const SweepArgs &args, cudaStream_t stream);
 
 // ---- statistics kernels (pz_stats.cu) ---------------------------------------

@@ -55,11 +55,11 @@ struct StoreS16 {
         sides2 = reinterpret_cast<uint32_t *>(slice + align16((uint32_t)N * 2));
         sides_init = a.sides2;
     }
-    __device__ void init(int lane) {
+    __device__ void init(int tid, int nthr) {
         uint32_t *v32 = reinterpret_cast<uint32_t *>(val);
-        for (int i = lane; i < (N + 1) / 2; i += 32) v32[i] = 0x80008000u;
+        for (int i = tid; i < (N + 1) / 2; i += nthr) v32[i] = 0x80008000u;
         if (sides_init)
-            for (int i = lane; i < (N + 15) / 16; i += 32) sides2[i] = sides_init[i];
+            for (int i = tid; i < (N + 15) / 16; i += nthr) sides2[i] = sides_init[i];
     }
     __device__ __forceinline__ uint32_t find(uint32_t x, uint32_t &tok) const {
         uint32_t vx = val[x];
@@ -115,28 +115,35 @@ struct StoreS16B {
         sides2 = reinterpret_cast<uint32_t *>(slice + off);
         sides_init = a.sides2;
     }
-    __device__ void init(int lane) {
+    __device__ void init(int tid, int nthr) {
         uint4 *v128 = reinterpret_cast<uint4 *>(val);
         const int n128 = (N * 2 + 15) / 16;
-        for (int i = lane; i < n128; i += 32) v128[i] = make_uint4(0, 0, 0, 0);
-        for (int i = lane; i < (N + 31) / 32; i += 32) rootbits[i] = 0xffffffffu;
+        for (int i = tid; i < n128; i += nthr) v128[i] = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < (N + 31) / 32; i += nthr) rootbits[i] = 0xffffffffu;
         if (sides_init)
-            for (int i = lane; i < (N + 15) / 16; i += 32) sides2[i] = sides_init[i];
+            for (int i = tid; i < (N + 15) / 16; i += nthr) sides2[i] = sides_init[i];
     }
     __device__ __forceinline__ bool is_root(uint32_t x) const {
         return (rootbits[x >> 5] >> (x & 31u)) & 1u;
     }
+    // The root bit is always read BEFORE the value (compiler barrier; shared
+    // memory accesses of one warp are performed in issue order) and unite()
+    // writes the parent pointer BEFORE clearing the bit, so a concurrent
+    // reader that sees "not a root" always reads a parent pointer, never a size.
     __device__ __forceinline__ uint32_t find(uint32_t x, uint32_t &tok) const {
         bool rx = is_root(x);
+        asm volatile("" ::: "memory");
         uint32_t vx = val[x];
         while (!rx) {
             const uint32_t p = vx;
             const bool rp = is_root(p);
+            asm volatile("" ::: "memory");
             const uint32_t vp = val[p];
             if (rp) { x = p; vx = vp; break; }
             val[x] = (uint16_t)vp;
             x = vp;
             rx = is_root(x);
+            asm volatile("" ::: "memory");
             vx = val[x];
         }
         tok = vx;
@@ -151,8 +158,9 @@ struct StoreS16B {
         const uint32_t sa = ta, sb = tb;
         const uint32_t big = sa >= sb ? ra : rb, small = sa >= sb ? rb : ra;
         val[small] = (uint16_t)big;
-        atomicAnd(&rootbits[small >> 5], ~(1u << (small & 31u)));
         val[big] = (uint16_t)(sa + sb + 1);
+        __threadfence_block();
+        atomicAnd(&rootbits[small >> 5], ~(1u << (small & 31u)));
         uint32_t m = 0;
         if (track) {
             const uint32_t mb = side_of(big);
@@ -176,8 +184,8 @@ struct StoreG32 {
         val = a.gscratch + (size_t)gwarp * (size_t)a.N;
         sides_init = a.sides2;
     }
-    __device__ void init(int lane) {
-        for (int i = lane; i < N; i += 32) {
+    __device__ void init(int tid, int nthr) {
+        for (int i = tid; i < N; i += nthr) {
             uint32_t s = sides_init ? (sides_init[i >> 4] >> ((i & 15) * 2)) & 3u : 0u;
             val[i] = 0x80000000u | (s << 29);
         }
@@ -216,6 +224,78 @@ __device__ __forceinline__ uint32_t claim_slot(uint32_t r, int log2) {
     return (r * 0x9E3779B1u) >> (32 - log2);
 }
 
+// ---------------------------------------------------------------------------
+// merge phase of one batch (warp-wide): on entry every valid lane holds the
+// TRUE roots (ru, rv) of its bond's endpoints and their tokens.  Returns the
+// lane's merge record; span_n = row at which the sides got joined (or NEVER).
+// ---------------------------------------------------------------------------
+template <class Store>
+__device__ __forceinline__ typename Store::Rec
+merge_batch(Store &st, uint32_t *claim, int clog, int lane, bool valid, int n, uint32_t ru,
+            uint32_t tu, uint32_t rv, uint32_t tv, bool track, int any3, uint32_t &span_n)
+{
+    using Rec = typename Store::Rec;
+    const bool cand = valid && ru != rv;
+    const uint32_t cmask = __ballot_sync(0xffffffffu, cand);
+    Rec rec = 0;
+    span_n = NSPAN_NEVER;
+    if (!cmask) return rec;
+    __syncwarp();
+    uint32_t remaining = cmask;
+    const int ncand = __popc(cmask);
+    bool win = false;
+    if (ncand <= 2) {
+        // the first candidate can always go; the second one too unless it
+        // shares a root with the first
+        const int l0 = __ffs(cmask) - 1;
+        const uint32_t a0 = __shfl_sync(0xffffffffu, ru, l0), b0 = __shfl_sync(0xffffffffu, rv, l0);
+        win = cand && (lane == l0 || (ru != a0 && ru != b0 && rv != a0 && rv != b0));
+    } else {
+        // claim round: order-safe parallel merges
+        uint32_t su = 0, sv = 0;
+        if (cand) {
+            su = claim_slot(ru, clog);
+            sv = claim_slot(rv, clog);
+            atomicMin(&claim[su], (uint32_t)lane);
+            atomicMin(&claim[sv], (uint32_t)lane);
+        }
+        __syncwarp();
+        win = cand && claim[su] == (uint32_t)lane && claim[sv] == (uint32_t)lane;
+        __syncwarp();
+        if (cand) { claim[su] = CLAIM_FREE; claim[sv] = CLAIM_FREE; }
+    }
+    if (win) {
+        rec = make_rec<Rec>(Store::size_m1(tu), Store::size_m1(tv));
+        const uint32_t m = st.unite(ru, tu, rv, tv, track);
+        if (track && (m == 3u || any3)) span_n = (uint32_t)n + 1;
+    }
+    remaining = cmask & ~__ballot_sync(0xffffffffu, win);
+    __syncwarp();
+    // replay of the dependent merges in bond order, the warp walking together
+    while (remaining) {
+        const int l = __ffs(remaining) - 1;
+        remaining &= remaining - 1;
+        uint32_t ta, tb;
+        const uint32_t ra = st.find(__shfl_sync(0xffffffffu, ru, l), ta);
+        const uint32_t rb = st.find(__shfl_sync(0xffffffffu, rv, l), tb);
+        if (ra != rb) {
+            // all lanes perform the same (idempotent) writes
+            const uint32_t m = st.unite(ra, ta, rb, tb, track);
+            if (lane == l) {
+                rec = make_rec<Rec>(Store::size_m1(ta), Store::size_m1(tb));
+                if (track && (m == 3u || any3)) span_n = (uint32_t)n + 1;
+            }
+        }
+        __syncwarp();
+    }
+    if (track) span_n = __reduce_min_sync(0xffffffffu, span_n);
+    return rec;
+}
+
+// ---------------------------------------------------------------------------
+// single-warp kernel: one warp = one run (kept for small graphs and as the
+// A/B baseline of the team kernel below)
+// ---------------------------------------------------------------------------
 template <class Store>
 __global__ void sweep_kernel(SweepArgs a, uint32_t slice_bytes)
 {
@@ -239,7 +319,7 @@ __global__ void sweep_kernel(SweepArgs a, uint32_t slice_bytes)
     const bool spanning = a.sides2 != nullptr;
 
     for (int run = gwarp; run < a.R; run += nwarps) {
-        st.init(lane);
+        st.init(lane, 32);
         __syncwarp();
         const int32_t *perm = a.perms + (size_t)run * M;
         Rec *rec_out = reinterpret_cast<Rec *>(a.recs) + (size_t)run * M;
@@ -266,56 +346,10 @@ __global__ void sweep_kernel(SweepArgs a, uint32_t slice_bytes)
                 ru = st.find(u, tu);
                 rv = st.find(v, tv);
             }
-            const bool cand = valid && ru != rv;
-            const uint32_t cmask = __ballot_sync(0xffffffffu, cand);
-            Rec rec = 0;
-            if (cmask) {
-                __syncwarp();
-                uint32_t span_n = NSPAN_NEVER;
-                uint32_t remaining = cmask;
-                if (__popc(cmask) > 2) {
-                    // ---- claim round: order-safe parallel merges ---------------
-                    uint32_t su = 0, sv = 0;
-                    if (cand) {
-                        su = claim_slot(ru, clog);
-                        sv = claim_slot(rv, clog);
-                        atomicMin(&claim[su], (uint32_t)lane);
-                        atomicMin(&claim[sv], (uint32_t)lane);
-                    }
-                    __syncwarp();
-                    const bool win = cand && claim[su] == (uint32_t)lane && claim[sv] == (uint32_t)lane;
-                    __syncwarp();
-                    if (cand) { claim[su] = CLAIM_FREE; claim[sv] = CLAIM_FREE; }
-                    if (win) {
-                        rec = make_rec<Rec>(Store::size_m1(tu), Store::size_m1(tv));
-                        const uint32_t m = st.unite(ru, tu, rv, tv, track);
-                        if (track && (m == 3u || a.any3)) span_n = (uint32_t)n + 1;
-                    }
-                    remaining = cmask & ~__ballot_sync(0xffffffffu, win);
-                    __syncwarp();
-                }
-                // ---- replay of the dependent merges in bond order ------------
-                while (remaining) {
-                    const int l = __ffs(remaining) - 1;
-                    remaining &= remaining - 1;
-                    uint32_t ta, tb;
-                    const uint32_t ra = st.find(__shfl_sync(0xffffffffu, ru, l), ta);
-                    const uint32_t rb = st.find(__shfl_sync(0xffffffffu, rv, l), tb);
-                    if (ra != rb) {
-                        // all lanes perform the same (idempotent) writes
-                        const uint32_t m = st.unite(ra, ta, rb, tb, track);
-                        if (lane == l) {
-                            rec = make_rec<Rec>(Store::size_m1(ta), Store::size_m1(tb));
-                            if (track && (m == 3u || a.any3)) span_n = (uint32_t)n + 1;
-                        }
-                    }
-                    __syncwarp();
-                }
-                if (track) {
-                    span_n = __reduce_min_sync(0xffffffffu, span_n);
-                    if (span_n != NSPAN_NEVER) { nspan = span_n; track = false; }
-                }
-            }
+            uint32_t span_n;
+            const Rec rec = merge_batch(st, claim, clog, lane, valid, n, ru, tu, rv, tv, track,
+                                        a.any3, span_n);
+            if (track && span_n != NSPAN_NEVER) { nspan = span_n; track = false; }
             if (valid) __stcs(&rec_out[n], rec);
         }
         if (lane == 0) a.nspan[run] = nspan;
@@ -324,11 +358,164 @@ __global__ void sweep_kernel(SweepArgs a, uint32_t slice_bytes)
 }
 
 // ---------------------------------------------------------------------------
+// team kernel: one CTA of 4 warps = one run.  Three FINDER warps run ahead of
+// the MERGER warp: finder j takes batches j, j+3, ... , resolves both endpoints
+// of its 32 bonds to (possibly slightly stale) cluster representatives with
+// path-halving finds, and posts them in a shared-memory ring.  The merger
+// consumes the batches in order, walks each representative up to the current
+// root (usually zero or one hop), and performs the order-safe merges.
+//
+// Why stale representatives are safe: a finder only ever returns a node that
+// was an ancestor-or-self of the endpoint when it was read, and ancestors stay
+// ancestors (links are only added at roots, by the merger); halving writes
+// replace a parent by an ancestor and never touch a root.  The finds -- two
+// thirds of the instructions of a batch -- thereby leave the critical path
+// and run on the other three warp schedulers of the SM.
+// ---------------------------------------------------------------------------
+static constexpr int TEAM_FINDERS = 3;
+static constexpr int TEAM_THREADS = 32 * (TEAM_FINDERS + 1);
+static constexpr int RING = 8;
+
+__device__ __forceinline__ uint32_t ld_volatile(const uint32_t *p) { return *(const volatile uint32_t *)p; }
+__device__ __forceinline__ void st_volatile(uint32_t *p, uint32_t v) { *(volatile uint32_t *)p = v; }
+__device__ __forceinline__ uint32_t pack_pair(uint32_t a, uint32_t b, uint32_t) { return a | (b << 16); }
+__device__ __forceinline__ uint2 pack_pair(uint32_t a, uint32_t b, uint2) { return make_uint2(a, b); }
+__device__ __forceinline__ uint32_t ld_pair(const uint32_t *p) { return *(const volatile uint32_t *)p; }
+__device__ __forceinline__ uint2 ld_pair(const uint2 *p) {
+    const volatile uint32_t *q = reinterpret_cast<const volatile uint32_t *>(p);
+    return make_uint2(q[0], q[1]);
+}
+
+template <class Store>
+__global__ void __launch_bounds__(TEAM_THREADS, 4) sweep_team_kernel(SweepArgs a, uint32_t store_bytes)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    using Rec = typename Store::Rec;
+    using Edge = typename Store::Edge;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int M = a.M;
+    const int clog = a.claim_log2;
+    const int nb = (M + 31) / 32;
+
+    uint32_t *claim = reinterpret_cast<uint32_t *>(smem);
+    unsigned char *p = smem + (sizeof(uint32_t) << clog);
+    Store st;
+    st.bind(p, a, blockIdx.x);
+    p += store_bytes;
+    Edge *ring = reinterpret_cast<Edge *>(p);                 // [RING][32]
+    p += sizeof(Edge) * RING * 32;
+    uint32_t *ready = reinterpret_cast<uint32_t *>(p);        // [RING] batch number + 1
+    uint32_t *done = ready + RING;                            // batches consumed by the merger
+
+    for (int i = threadIdx.x; i < (1 << clog); i += TEAM_THREADS) claim[i] = CLAIM_FREE;
+    const Edge *edges = reinterpret_cast<const Edge *>(a.edges);
+    const bool spanning = a.sides2 != nullptr;
+
+    for (int run = blockIdx.x; run < a.R; run += gridDim.x) {
+        st.init(threadIdx.x, TEAM_THREADS);
+        if (threadIdx.x < RING) ready[threadIdx.x] = 0;
+        if (threadIdx.x == RING) *done = 0;
+        __syncthreads();
+        const int32_t *perm = a.perms + (size_t)run * M;
+
+        if (warp < TEAM_FINDERS) {
+            // ---------------- finder ----------------
+            Edge uv_next = Edge();
+            int32_t e_next = 0;
+            {
+                const int n1 = warp * 32 + lane, n2 = n1 + TEAM_FINDERS * 32;
+                if (n1 < M) uv_next = __ldg(&edges[__ldcs(&perm[n1])]);
+                if (n2 < M) e_next = __ldcs(&perm[n2]);
+            }
+            for (int b = warp; b < nb; b += TEAM_FINDERS) {
+                const int n = b * 32 + lane;
+                const Edge uv = uv_next;
+                if (n + TEAM_FINDERS * 32 < M) uv_next = __ldg(&edges[e_next]);
+                if (n + 2 * TEAM_FINDERS * 32 < M) e_next = __ldcs(&perm[n + 2 * TEAM_FINDERS * 32]);
+                // ring slot b % RING is free once the merger has taken batch b - RING
+                while ((int)ld_volatile(done) < b - RING + 1) __nanosleep(40);
+                uint32_t ru = 0, rv = 0, t;
+                if (n < M) {
+                    uint32_t u, v;
+                    edge_uv(uv, u, v);
+                    ru = st.find(u, t);
+                    rv = st.find(v, t);
+                }
+                ring[(b % RING) * 32 + lane] = pack_pair(ru, rv, Edge());
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence_block();
+                    st_volatile(&ready[b % RING], (uint32_t)b + 1);
+                }
+            }
+        } else {
+            // ---------------- merger ----------------
+            Rec *rec_out = reinterpret_cast<Rec *>(a.recs) + (size_t)run * M;
+            uint32_t nspan = NSPAN_NEVER;
+            bool track = spanning;
+            for (int b = 0; b < nb; ++b) {
+                const int slot = b % RING;
+                while (ld_volatile(&ready[slot]) != (uint32_t)b + 1) __nanosleep(20);
+                __threadfence_block();
+                const Edge pr = ld_pair(&ring[slot * 32 + lane]);
+                __syncwarp();
+                if (lane == 0) st_volatile(done, (uint32_t)b + 1);
+                const int n = b * 32 + lane;
+                const bool valid = n < M;
+                uint32_t ru = 0, rv = 0, tu = 0, tv = 0;
+                if (valid) {
+                    uint32_t x, y;
+                    edge_uv(pr, x, y);
+                    ru = st.find(x, tu);
+                    rv = st.find(y, tv);
+                }
+                uint32_t span_n;
+                const Rec rec = merge_batch(st, claim, clog, lane, valid, n, ru, tu, rv, tv, track,
+                                            a.any3, span_n);
+                if (track && span_n != NSPAN_NEVER) { nspan = span_n; track = false; }
+                if (valid) __stcs(&rec_out[n], rec);
+            }
+            if (lane == 0) a.nspan[run] = nspan;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
 // planning and launch
 // ---------------------------------------------------------------------------
 static int ilog2_ceil(uint32_t x) { int l = 0; while ((1u << l) < x) ++l; return l; }
 
-SweepPlan plan_sweep(int32_t N, int32_t R, int sms, size_t smem_optin, int force_kind)
+static SweepPlan plan_team(SweepPlan p, int32_t N, int32_t R, int sms, size_t smem_optin,
+                           size_t store_bytes)
+{
+    // one CTA of TEAM_THREADS per run; as many CTAs per SM as shared memory and
+    // the 64-warp limit allow
+    const size_t sm_total = 228 * 1024;
+    const size_t edge_bytes = p.kind == STORE_G32 ? 8 : 4;
+    int clog = p.claim_log2;
+    size_t fixed = store_bytes + edge_bytes * RING * 32 + 4 * (RING + 1) + 16;
+    while (clog > 8 && fixed + ((size_t)4 << clog) > smem_optin) --clog;
+    p.claim_log2 = clog;
+    p.team = 1;
+    p.store_bytes = store_bytes;
+    p.warps_per_cta = TEAM_FINDERS + 1;
+    p.smem_bytes = align16h(fixed + ((size_t)4 << clog));
+    p.slice_bytes = p.smem_bytes;
+    int ctas_per_sm = (int)(sm_total / (p.smem_bytes + 1024));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    if (ctas_per_sm > 64 / (TEAM_FINDERS + 1)) ctas_per_sm = 64 / (TEAM_FINDERS + 1);
+    if (p.kind == STORE_G32 && ctas_per_sm > 4) ctas_per_sm = 4;
+    long long grid = (long long)sms * ctas_per_sm;
+    if (grid > R) grid = R;
+    if (grid < 1) grid = 1;
+    p.grid = (int)grid;
+    p.gscratch_bytes = p.kind == STORE_G32 ? (size_t)p.grid * (size_t)N * 4 : 0;
+    return p;
+}
+
+SweepPlan plan_sweep(int32_t N, int32_t R, int sms, size_t smem_optin, int force_kind, int team)
 {
     SweepPlan p{};
     const size_t budget = smem_optin;          // per CTA (opt-in maximum)
@@ -347,6 +534,7 @@ SweepPlan plan_sweep(int32_t N, int32_t R, int sms, size_t smem_optin, int force
     if (clog > clog_max) clog = clog_max;
     while (clog > 8 && store_bytes + ((size_t)4 << clog) > budget) --clog;
     p.claim_log2 = clog;
+    if (team) return plan_team(p, N, R, sms, smem_optin, align16h(store_bytes));
     p.slice_bytes = align16h(store_bytes + ((size_t)4 << clog));
 
     // warps (runs in flight) per CTA and CTAs per SM: as many runs as shared
@@ -381,6 +569,17 @@ SweepPlan plan_sweep(int32_t N, int32_t R, int sms, size_t smem_optin, int force
 }
 
 template <class Store>
+static cudaError_t launch_team_t(const SweepPlan &p, const SweepArgs &a, cudaStream_t s)
+{
+    cudaError_t e = cudaFuncSetAttribute(sweep_team_kernel<Store>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)p.smem_bytes);
+    if (e != cudaSuccess) return e;
+    sweep_team_kernel<Store><<<p.grid, TEAM_THREADS, p.smem_bytes, s>>>(a, (uint32_t)p.store_bytes);
+    return cudaGetLastError();
+}
+
+template <class Store>
 static cudaError_t launch_t(const SweepPlan &p, const SweepArgs &a, cudaStream_t s)
 {
     cudaError_t e = cudaFuncSetAttribute(sweep_kernel<Store>,
@@ -393,6 +592,13 @@ static cudaError_t launch_t(const SweepPlan &p, const SweepArgs &a, cudaStream_t
 
 cudaError_t launch_sweep(const SweepPlan &p, const SweepArgs &a, cudaStream_t s)
 {
+    if (p.team) {
+        switch (p.kind) {
+        case STORE_S16: return launch_team_t<StoreS16>(p, a, s);
+        case STORE_S16B: return launch_team_t<StoreS16B>(p, a, s);
+        default: return launch_team_t<StoreG32>(p, a, s);
+        }
+    }
     switch (p.kind) {
     case STORE_S16: return launch_t<StoreS16>(p, a, s);
     case STORE_S16B: return launch_t<StoreS16B>(p, a, s);

@@ -142,7 +142,7 @@ def bond_sample_states(
         ``spanning_cluster`` is True but ``spanning_sides`` does not hold
         exactly two sides.
     '''
-    if spanning_cluster:
+    if spanning_cluster and not isinstance(perc_graph, _lowering.LoweredGraph):
         if len(spanning_sides) != 2:
             raise ValueError(
                 'Spanning cluster is to be detected, but auxiliary nodes '
@@ -178,12 +178,6 @@ def bond_microcanonical_statistics(
     Drop-in for percolate/hpc.py:310-404: the structured array of all
     ``num_edges + 1`` states of one run, fields as in ``bond_sample_states``.
     """
-    if spanning_cluster:
-        if spanning_sides is None or len(spanning_sides) != 2:
-            raise ValueError(
-                'Spanning cluster is to be detected, but auxiliary nodes '
-                'of less or more than 2 types (sides) given.'
-            )
     lowered = _lower(perc_graph, spanning_cluster, auxiliary_node_attributes,
                      auxiliary_edge_attributes, spanning_sides)
     if lowered.num_nodes != num_nodes or lowered.num_edges != num_edges:

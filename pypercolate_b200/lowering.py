@@ -106,19 +106,23 @@ def lower(perc_graph, spanning_cluster=True, auxiliary_node_attributes=None,
     Raises the reference's ``ValueError`` when ``spanning_sides`` does not hold
     exactly two sides (percolate/hpc.py:197-202).
     """
+    if isinstance(perc_graph, LoweredGraph):
+        # already lowered: the two sides are the bits of its side mask
+        if spanning_cluster and perc_graph.side_mask is None:
+            raise ValueError(
+                'Spanning cluster is to be detected, but auxiliary nodes '
+                'of less or more than 2 types (sides) given.'
+            )
+        return perc_graph if spanning_cluster else (
+            perc_graph if perc_graph.side_mask is None
+            else perc_graph.without_spanning())
+
     if spanning_cluster:
         if spanning_sides is None or len(spanning_sides) != 2:
             raise ValueError(
                 'Spanning cluster is to be detected, but auxiliary nodes '
                 'of less or more than 2 types (sides) given.'
             )
-
-    if isinstance(perc_graph, LoweredGraph):
-        if spanning_cluster and perc_graph.side_mask is None:
-            raise ValueError("LoweredGraph carries no spanning sides")
-        return perc_graph if spanning_cluster else (
-            perc_graph if perc_graph.side_mask is None
-            else perc_graph.without_spanning())
 
     cache = getattr(perc_graph, "__dict__", {}).get(_LOWER_CACHE_ATTR)
     key = (bool(spanning_cluster), id(auxiliary_node_attributes),

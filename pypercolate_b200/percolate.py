@@ -95,9 +95,7 @@ _GRAPH_CACHE_ATTR = '_pz_percolation'
 def _prepare(graph, spanning_cluster):
     """(LoweredGraph, list of bonds as node pairs) for ``graph``."""
     if isinstance(graph, _lowering.LoweredGraph):
-        lowered = _lowering.lower(graph, spanning_cluster=spanning_cluster,
-                                  spanning_sides=[0, 1])
-        return lowered
+        return _lowering.lower(graph, spanning_cluster=spanning_cluster)
     cache = getattr(graph, '__dict__', {}).get(_GRAPH_CACHE_ATTR)
     key = (bool(spanning_cluster), graph.number_of_nodes(),
            graph.number_of_edges())

@@ -242,7 +242,15 @@ def test_canonical_chain_matches_reference_golden(name):
         # std / ci inherit the absolute accuracy of sqrt(M2): scale with the mean
         base = f.rsplit('_', 1)[0] + '_mean'
         scale = np.nanmax(np.abs(ref_fin[base])) if base in ref_fin.dtype.names else 0.0
-        np.testing.assert_allclose(fin[f], ref_fin[f], rtol=1e-8, atol=1e-12 * scale, equal_nan=True)
+        got, want = fin[f].copy(), ref_fin[f].copy()
+        if f.endswith('_ci'):
+            # scipy returns NaN bounds when the runs agree to the last bit (std == 0); whether
+            # they do depends on summation order, so a NaN bound is equivalent to the mean
+            mean_g = np.broadcast_to(fin[base][..., None], got.shape)
+            mean_w = np.broadcast_to(ref_fin[base][..., None], want.shape)
+            got = np.where(np.isnan(got), mean_g, got)
+            want = np.where(np.isnan(want), mean_w, want)
+        np.testing.assert_allclose(got, want, rtol=1e-8, atol=1e-12 * scale, equal_nan=True)
     ctx.close()
 
 
