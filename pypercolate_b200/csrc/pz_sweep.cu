@@ -2,7 +2,8 @@
 //
 // Replaces the hot loop of the reference, percolate/hpc.py:249-307 (twin:
 // percolate/percolate.py:298-356): one Python iteration per bond over a dict
-// union-find.  Here ONE WARP owns one run and adds bonds 32 at a time:
+// union-find.  Here one CTA (or, in the A/B baseline kernel, one warp) owns one
+// run and adds bonds a batch at a time:
 //
 //   1. every lane looks up the endpoints of its bond and finds both roots in
 //      parallel (weighted quick-union, path halving).  Concurrent halving
@@ -27,6 +28,9 @@
 namespace pz {
 
 static constexpr uint32_t CLAIM_FREE = 0xffffffffu;
+#ifndef PZ_STRICT_FENCE
+#define PZ_STRICT_FENCE 0
+#endif
 
 __device__ __forceinline__ uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 static inline size_t align16h(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -73,9 +77,26 @@ struct StoreS16 {
         tok = vx;
         return x;
     }
+    // walk two representatives up to their roots in lock step (no halving)
+    __device__ __forceinline__ void find2(uint32_t &x, uint32_t &y, uint32_t &tx, uint32_t &ty) const {
+        uint32_t vx = val[x], vy = val[y];
+        while (!(vx & vy & 0x8000u)) {
+            if (!(vx & 0x8000u)) x = vx;
+            if (!(vy & 0x8000u)) y = vy;
+            vx = val[x];
+            vy = val[y];
+        }
+        tx = vx; ty = vy;
+    }
     static __device__ __forceinline__ uint32_t size_m1(uint32_t tok) { return tok & 0x7fffu; }
     __device__ __forceinline__ uint32_t side_of(uint32_t r) const {
         return (sides2[r >> 4] >> ((r & 15u) * 2)) & 3u;
+    }
+    __device__ __forceinline__ uint32_t sides_of_root(uint32_t r, uint32_t) const { return side_of(r); }
+    __device__ __forceinline__ void make_child(uint32_t x, uint32_t parent) { val[x] = (uint16_t)parent; }
+    __device__ __forceinline__ void set_root(uint32_t r, uint32_t sz_m1, uint32_t add_sides) {
+        val[r] = (uint16_t)(0x8000u | sz_m1);
+        if (add_sides) atomicOr(&sides2[r >> 4], add_sides << ((r & 15u) * 2));
     }
     __device__ __forceinline__ uint32_t unite(uint32_t ra, uint32_t ta, uint32_t rb, uint32_t tb,
                                               bool track) {
@@ -149,9 +170,34 @@ struct StoreS16B {
         tok = vx;
         return x;
     }
+    __device__ __forceinline__ void find2(uint32_t &x, uint32_t &y, uint32_t &tx, uint32_t &ty) const {
+        bool rx = is_root(x), ry = is_root(y);
+        asm volatile("" ::: "memory");
+        uint32_t vx = val[x], vy = val[y];
+        while (!(rx && ry)) {
+            if (!rx) x = vx;
+            if (!ry) y = vy;
+            rx = is_root(x);
+            ry = is_root(y);
+            asm volatile("" ::: "memory");
+            vx = val[x];
+            vy = val[y];
+        }
+        tx = vx; ty = vy;
+    }
     static __device__ __forceinline__ uint32_t size_m1(uint32_t tok) { return tok; }
     __device__ __forceinline__ uint32_t side_of(uint32_t r) const {
         return (sides2[r >> 4] >> ((r & 15u) * 2)) & 3u;
+    }
+    __device__ __forceinline__ uint32_t sides_of_root(uint32_t r, uint32_t) const { return side_of(r); }
+    __device__ __forceinline__ void make_child(uint32_t x, uint32_t parent) {
+        val[x] = (uint16_t)parent;
+        asm volatile("" ::: "memory");
+        atomicAnd(&rootbits[x >> 5], ~(1u << (x & 31u)));
+    }
+    __device__ __forceinline__ void set_root(uint32_t r, uint32_t sz_m1, uint32_t add_sides) {
+        val[r] = (uint16_t)sz_m1;
+        if (add_sides) atomicOr(&sides2[r >> 4], add_sides << ((r & 15u) * 2));
     }
     __device__ __forceinline__ uint32_t unite(uint32_t ra, uint32_t ta, uint32_t rb, uint32_t tb,
                                               bool track) {
@@ -159,7 +205,11 @@ struct StoreS16B {
         const uint32_t big = sa >= sb ? ra : rb, small = sa >= sb ? rb : ra;
         val[small] = (uint16_t)big;
         val[big] = (uint16_t)(sa + sb + 1);
+#if PZ_STRICT_FENCE
         __threadfence_block();
+#else
+        asm volatile("" ::: "memory");     // shared-memory stores of a warp are performed in order
+#endif
         atomicAnd(&rootbits[small >> 5], ~(1u << (small & 31u)));
         uint32_t m = 0;
         if (track) {
@@ -202,7 +252,24 @@ struct StoreG32 {
         tok = vx;
         return x;
     }
+    __device__ __forceinline__ void find2(uint32_t &x, uint32_t &y, uint32_t &tx, uint32_t &ty) const {
+        uint32_t vx = val[x], vy = val[y];
+        while (!((vx & vy) >> 31)) {
+            if (!(vx >> 31)) x = vx;
+            if (!(vy >> 31)) y = vy;
+            vx = val[x];
+            vy = val[y];
+        }
+        tx = vx; ty = vy;
+    }
     static __device__ __forceinline__ uint32_t size_m1(uint32_t tok) { return tok & 0x1fffffffu; }
+    __device__ __forceinline__ uint32_t sides_of_root(uint32_t, uint32_t tok) const { return (tok >> 29) & 3u; }
+    __device__ __forceinline__ void make_child(uint32_t x, uint32_t parent) { val[x] = parent; }
+    __device__ __forceinline__ void set_root(uint32_t r, uint32_t sz_m1, uint32_t add_sides) {
+        // only the designated thread of a star round calls this: plain read-modify-write
+        const uint32_t old = val[r];
+        val[r] = 0x80000000u | (old & 0x60000000u) | (add_sides << 29) | sz_m1;
+    }
     __device__ __forceinline__ uint32_t unite(uint32_t ra, uint32_t ta, uint32_t rb, uint32_t tb,
                                               bool) {
         const uint32_t sa = size_m1(ta), sb = size_m1(tb);
@@ -225,68 +292,65 @@ __device__ __forceinline__ uint32_t claim_slot(uint32_t r, int log2) {
 }
 
 // ---------------------------------------------------------------------------
-// merge phase of one batch (warp-wide): on entry every valid lane holds the
-// TRUE roots (ru, rv) of its bond's endpoints and their tokens.  Returns the
-// lane's merge record; span_n = row at which the sides got joined (or NEVER).
+// merge phase of one batch (warp-wide).  On entry every valid lane holds
+// representatives (ancestors-or-self) of its bond's two endpoints.  Rounds:
+//   every pending lane walks its representatives up to the current roots;
+//   lanes whose roots differ are candidates; a candidate may merge now iff no
+//   LOWER pending candidate touches either of its roots (then all earlier
+//   bonds of the batch work on disjoint clusters, so the sizes it records are
+//   the ones the sequential reference sees); the rest retries next round.
+// The lowest pending candidate always merges, so the loop terminates.  With
+// one or two candidates the decision is made with shuffles, otherwise with
+// one atomicMin claim per root in a hashed shared-memory table (a hash
+// collision only delays a lane, it never breaks the order).
+// Returns the lane's merge record; span_n = first row at which the two
+// spanning sides are joined by a merge of this batch (or NSPAN_NEVER).
 // ---------------------------------------------------------------------------
 template <class Store>
 __device__ __forceinline__ typename Store::Rec
 merge_batch(Store &st, uint32_t *claim, int clog, int lane, bool valid, int n, uint32_t ru,
-            uint32_t tu, uint32_t rv, uint32_t tv, bool track, int any3, uint32_t &span_n)
+            uint32_t rv, bool track, int any3, uint32_t &span_n)
 {
     using Rec = typename Store::Rec;
-    const bool cand = valid && ru != rv;
-    const uint32_t cmask = __ballot_sync(0xffffffffu, cand);
     Rec rec = 0;
     span_n = NSPAN_NEVER;
-    if (!cmask) return rec;
-    __syncwarp();
-    uint32_t remaining = cmask;
-    const int ncand = __popc(cmask);
-    bool win = false;
-    if (ncand <= 2) {
-        // the first candidate can always go; the second one too unless it
-        // shares a root with the first
-        const int l0 = __ffs(cmask) - 1;
-        const uint32_t a0 = __shfl_sync(0xffffffffu, ru, l0), b0 = __shfl_sync(0xffffffffu, rv, l0);
-        win = cand && (lane == l0 || (ru != a0 && ru != b0 && rv != a0 && rv != b0));
-    } else {
-        // claim round: order-safe parallel merges
-        uint32_t su = 0, sv = 0;
-        if (cand) {
-            su = claim_slot(ru, clog);
-            sv = claim_slot(rv, clog);
-            atomicMin(&claim[su], (uint32_t)lane);
-            atomicMin(&claim[sv], (uint32_t)lane);
+    bool pending = valid;
+    for (;;) {
+        uint32_t tu = 0, tv = 0;
+        if (pending) {
+            st.find2(ru, rv, tu, tv);
+            pending = ru != rv;
         }
-        __syncwarp();
-        win = cand && claim[su] == (uint32_t)lane && claim[sv] == (uint32_t)lane;
-        __syncwarp();
-        if (cand) { claim[su] = CLAIM_FREE; claim[sv] = CLAIM_FREE; }
-    }
-    if (win) {
-        rec = make_rec<Rec>(Store::size_m1(tu), Store::size_m1(tv));
-        const uint32_t m = st.unite(ru, tu, rv, tv, track);
-        if (track && (m == 3u || any3)) span_n = (uint32_t)n + 1;
-    }
-    remaining = cmask & ~__ballot_sync(0xffffffffu, win);
-    __syncwarp();
-    // replay of the dependent merges in bond order, the warp walking together
-    while (remaining) {
-        const int l = __ffs(remaining) - 1;
-        remaining &= remaining - 1;
-        uint32_t ta, tb;
-        const uint32_t ra = st.find(__shfl_sync(0xffffffffu, ru, l), ta);
-        const uint32_t rb = st.find(__shfl_sync(0xffffffffu, rv, l), tb);
-        if (ra != rb) {
-            // all lanes perform the same (idempotent) writes
-            const uint32_t m = st.unite(ra, ta, rb, tb, track);
-            if (lane == l) {
-                rec = make_rec<Rec>(Store::size_m1(ta), Store::size_m1(tb));
-                if (track && (m == 3u || any3)) span_n = (uint32_t)n + 1;
+        const uint32_t cmask = __ballot_sync(0xffffffffu, pending);
+        if (!cmask) break;
+        const int ncand = __popc(cmask);
+        bool win;
+        if (ncand <= 2) {
+            const int l0 = __ffs(cmask) - 1;
+            const uint32_t a0 = __shfl_sync(0xffffffffu, ru, l0), b0 = __shfl_sync(0xffffffffu, rv, l0);
+            win = pending && (lane == l0 || (ru != a0 && ru != b0 && rv != a0 && rv != b0));
+        } else {
+            uint32_t su = 0, sv = 0;
+            if (pending) {
+                su = claim_slot(ru, clog);
+                sv = claim_slot(rv, clog);
+                atomicMin(&claim[su], (uint32_t)lane);
+                atomicMin(&claim[sv], (uint32_t)lane);
             }
+            __syncwarp();
+            win = pending && claim[su] == (uint32_t)lane && claim[sv] == (uint32_t)lane;
+            __syncwarp();
+            if (pending) { claim[su] = CLAIM_FREE; claim[sv] = CLAIM_FREE; }
         }
-        __syncwarp();
+        if (win) {
+            rec = make_rec<Rec>(Store::size_m1(tu), Store::size_m1(tv));
+            const uint32_t m = st.unite(ru, tu, rv, tv, track);
+            if (track && (m == 3u || any3)) span_n = (uint32_t)n + 1;
+            pending = false;
+        }
+        // every candidate merged: done (also orders the winners' writes
+        // before the next round's reads)
+        if (__ballot_sync(0xffffffffu, win) == cmask) break;
     }
     if (track) span_n = __reduce_min_sync(0xffffffffu, span_n);
     return rec;
@@ -339,16 +403,15 @@ __global__ void sweep_kernel(SweepArgs a, uint32_t slice_bytes)
             if (n + 32 < M) uv_next = __ldg(&edges[e_next]);
             if (n + 64 < M) e_next = __ldcs(&perm[n + 64]);
 
-            uint32_t ru = 0, rv = 0, tu = 0, tv = 0;
+            uint32_t ru = 0, rv = 0, t;
             if (valid) {
                 uint32_t u, v;
                 edge_uv(uv, u, v);
-                ru = st.find(u, tu);
-                rv = st.find(v, tv);
+                ru = st.find(u, t);
+                rv = st.find(v, t);
             }
             uint32_t span_n;
-            const Rec rec = merge_batch(st, claim, clog, lane, valid, n, ru, tu, rv, tv, track,
-                                        a.any3, span_n);
+            const Rec rec = merge_batch(st, claim, clog, lane, valid, n, ru, rv, track, a.any3, span_n);
             if (track && span_n != NSPAN_NEVER) { nspan = span_n; track = false; }
             if (valid) __stcs(&rec_out[n], rec);
         }
@@ -358,126 +421,183 @@ __global__ void sweep_kernel(SweepArgs a, uint32_t slice_bytes)
 }
 
 // ---------------------------------------------------------------------------
-// team kernel: one CTA of 4 warps = one run.  Three FINDER warps run ahead of
-// the MERGER warp: finder j takes batches j, j+3, ... , resolves both endpoints
-// of its 32 bonds to (possibly slightly stale) cluster representatives with
-// path-halving finds, and posts them in a shared-memory ring.  The merger
-// consumes the batches in order, walks each representative up to the current
-// root (usually zero or one hop), and performs the order-safe merges.
+// CTA kernel: one CTA = one run, every thread one bond of a batch of
+// CTA_THREADS bonds, all warps in lock step:
 //
-// Why stale representatives are safe: a finder only ever returns a node that
-// was an ancestor-or-self of the endpoint when it was read, and ancestors stay
-// ancestors (links are only added at roots, by the merger); halving writes
-// replace a parent by an ancestor and never touch a root.  The finds -- two
-// thirds of the instructions of a batch -- thereby leave the critical path
-// and run on the other three warp schedulers of the SM.
+//   find    every thread resolves both endpoints of its bond (path halving;
+//           no merges are in flight, so concurrent halving is benign)
+//   round   pending threads (roots differ) post an atomicMin claim, keyed by
+//           their position in the batch, on the hashed slot of each root;
+//           barrier; a thread whose two slots carry its own key merges -- no
+//           earlier bond of the batch touches its clusters, so the sizes it
+//           records are the sequential ones; barrier; losers walk up to the new
+//           roots and go again.  The earliest pending bond always wins.
+//   star    bonds that join a cluster to the current largest cluster (the
+//           HUB) would serialise, one per round, once the giant cluster exists.
+//           They claim only their other root; if every earlier pending bond
+//           of the batch has merged or merges in this round, they all merge
+//           at once and a block-wide ordered prefix sum of the attached sizes
+//           gives each of them the hub size the sequential order would see.
+//
+// Claim keys carry a decreasing epoch in their upper bits, so claims of earlier
+// rounds never need to be cleared.  The four warp schedulers of the SM work on
+// the same run, and every dependent-latency chain (find, claim, merge) is paid
+// once per CTA_THREADS bonds instead of once per 32.
 // ---------------------------------------------------------------------------
-static constexpr int TEAM_FINDERS = 3;
-static constexpr int TEAM_THREADS = 32 * (TEAM_FINDERS + 1);
-static constexpr int RING = 8;
+static constexpr int CTA_WARPS = 4;
+static constexpr int CTA_THREADS = 32 * CTA_WARPS;
 
-__device__ __forceinline__ uint32_t ld_volatile(const uint32_t *p) { return *(const volatile uint32_t *)p; }
-__device__ __forceinline__ void st_volatile(uint32_t *p, uint32_t v) { *(volatile uint32_t *)p = v; }
-__device__ __forceinline__ uint32_t pack_pair(uint32_t a, uint32_t b, uint32_t) { return a | (b << 16); }
-__device__ __forceinline__ uint2 pack_pair(uint32_t a, uint32_t b, uint2) { return make_uint2(a, b); }
-__device__ __forceinline__ uint32_t ld_pair(const uint32_t *p) { return *(const volatile uint32_t *)p; }
-__device__ __forceinline__ uint2 ld_pair(const uint2 *p) {
-    const volatile uint32_t *q = reinterpret_cast<const volatile uint32_t *>(p);
-    return make_uint2(q[0], q[1]);
-}
+struct CtaShared {
+    unsigned long long hub_key;               // (size << 32) | root of the largest cluster seen
+    unsigned long long scan_tot[CTA_WARPS];
+    uint32_t span_min;
+    uint32_t bmin;                            // lowest blocked position of the round
+};
 
 template <class Store>
-__global__ void __launch_bounds__(TEAM_THREADS, 4) sweep_team_kernel(SweepArgs a, uint32_t store_bytes)
+__global__ void __launch_bounds__(CTA_THREADS, 4) sweep_cta_kernel(SweepArgs a, uint32_t store_bytes)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     using Rec = typename Store::Rec;
     using Edge = typename Store::Edge;
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int M = a.M;
     const int clog = a.claim_log2;
-    const int nb = (M + 31) / 32;
 
     uint32_t *claim = reinterpret_cast<uint32_t *>(smem);
     unsigned char *p = smem + (sizeof(uint32_t) << clog);
     Store st;
     st.bind(p, a, blockIdx.x);
-    p += store_bytes;
-    Edge *ring = reinterpret_cast<Edge *>(p);                 // [RING][32]
-    p += sizeof(Edge) * RING * 32;
-    uint32_t *ready = reinterpret_cast<uint32_t *>(p);        // [RING] batch number + 1
-    uint32_t *done = ready + RING;                            // batches consumed by the merger
+    CtaShared *sh = reinterpret_cast<CtaShared *>(p + store_bytes);
 
-    for (int i = threadIdx.x; i < (1 << clog); i += TEAM_THREADS) claim[i] = CLAIM_FREE;
     const Edge *edges = reinterpret_cast<const Edge *>(a.edges);
     const bool spanning = a.sides2 != nullptr;
 
     for (int run = blockIdx.x; run < a.R; run += gridDim.x) {
-        st.init(threadIdx.x, TEAM_THREADS);
-        if (threadIdx.x < RING) ready[threadIdx.x] = 0;
-        if (threadIdx.x == RING) *done = 0;
+        st.init(tid, CTA_THREADS);
+        for (int i = tid; i < (1 << clog); i += CTA_THREADS) claim[i] = CLAIM_FREE;
+        if (tid == 0) {
+            sh->span_min = NSPAN_NEVER;
+            sh->bmin = 0xffffffffu;
+            sh->hub_key = 1ull << 32;          // node 0, size 1
+        }
         __syncthreads();
         const int32_t *perm = a.perms + (size_t)run * M;
+        Rec *rec_out = reinterpret_cast<Rec *>(a.recs) + (size_t)run * M;
+        bool track = spanning;                 // CTA-uniform
+        uint32_t epoch = 0x00ffffffu;          // decreasing: newer claims always win over stale ones
 
-        if (warp < TEAM_FINDERS) {
-            // ---------------- finder ----------------
-            Edge uv_next = Edge();
-            int32_t e_next = 0;
-            {
-                const int n1 = warp * 32 + lane, n2 = n1 + TEAM_FINDERS * 32;
-                if (n1 < M) uv_next = __ldg(&edges[__ldcs(&perm[n1])]);
-                if (n2 < M) e_next = __ldcs(&perm[n2]);
+        // two-deep software pipeline: perm[n] -> edges[perm[n]] -> use
+        Edge uv_next = Edge();
+        int32_t e_next = 0;
+        if (tid < M) uv_next = __ldg(&edges[__ldcs(&perm[tid])]);
+        if (tid + CTA_THREADS < M) e_next = __ldcs(&perm[tid + CTA_THREADS]);
+
+        for (int n0 = 0; n0 < M; n0 += CTA_THREADS) {
+            const int n = n0 + tid;            // bond index; row index is n + 1
+            const bool valid = n < M;
+            const Edge uv = uv_next;
+            if (n + CTA_THREADS < M) uv_next = __ldg(&edges[e_next]);
+            if (n + 2 * CTA_THREADS < M) e_next = __ldcs(&perm[n + 2 * CTA_THREADS]);
+
+            uint32_t ru = 0, rv = 0, tu = 0, tv = 0;
+            if (valid) {
+                uint32_t u, v;
+                edge_uv(uv, u, v);
+                ru = st.find(u, tu);
+                rv = st.find(v, tv);
             }
-            for (int b = warp; b < nb; b += TEAM_FINDERS) {
-                const int n = b * 32 + lane;
-                const Edge uv = uv_next;
-                if (n + TEAM_FINDERS * 32 < M) uv_next = __ldg(&edges[e_next]);
-                if (n + 2 * TEAM_FINDERS * 32 < M) e_next = __ldcs(&perm[n + 2 * TEAM_FINDERS * 32]);
-                // ring slot b % RING is free once the merger has taken batch b - RING
-                while ((int)ld_volatile(done) < b - RING + 1) __nanosleep(40);
-                uint32_t ru = 0, rv = 0, t;
-                if (n < M) {
-                    uint32_t u, v;
-                    edge_uv(uv, u, v);
-                    ru = st.find(u, t);
-                    rv = st.find(v, t);
+            bool pending = valid && ru != rv;
+            Rec rec = 0;
+            for (;;) {
+                const uint32_t key = (epoch << 8) | (uint32_t)tid;
+                const uint32_t hub = (uint32_t)sh->hub_key;
+                // star bond: one side is the hub; o = the other root
+                const bool star = pending && (ru == hub || rv == hub);
+                const uint32_t o = ru == hub ? rv : ru, to = ru == hub ? tv : tu;
+                const uint32_t th = ru == hub ? tu : tv;
+                uint32_t su = 0, sv = 0;
+                if (pending) {
+                    su = claim_slot(star ? o : ru, clog);
+                    sv = claim_slot(star ? o : rv, clog);
+                    atomicMin(&claim[su], key);
+                    if (!star) atomicMin(&claim[sv], key);
                 }
-                ring[(b % RING) * 32 + lane] = pack_pair(ru, rv, Edge());
-                __syncwarp();
-                if (lane == 0) {
-                    __threadfence_block();
-                    st_volatile(&ready[b % RING], (uint32_t)b + 1);
+                if (!__syncthreads_or(pending)) break;          // nothing (left) to merge
+                const bool own = pending && claim[su] == key && claim[sv] == key;
+                if (pending && !own) atomicMin(&sh->bmin, (uint32_t)tid);
+                const int nstar = __syncthreads_count(own && star);
+                bool won = false;
+                if (own && !star) {
+                    rec = make_rec<Rec>(Store::size_m1(tu), Store::size_m1(tv));
+                    const uint32_t sz = Store::size_m1(tu) + Store::size_m1(tv) + 2;
+                    const uint32_t m = st.unite(ru, tu, rv, tv, track);
+                    if (track && (m == 3u || a.any3)) atomicMin(&sh->span_min, (uint32_t)n + 1);
+                    const uint32_t big = Store::size_m1(tu) >= Store::size_m1(tv) ? ru : rv;
+                    const unsigned long long hk = ((unsigned long long)sz << 32) | big;
+                    if (hk > sh->hub_key) atomicMax(&sh->hub_key, hk);
+                    won = true;
+                }
+                if (nstar) {
+                    // star bonds merge together iff no earlier bond of the batch is blocked
+                    const bool sw = own && star && (uint32_t)tid < sh->bmin;
+                    const uint32_t so = sw ? st.sides_of_root(o, to) : 0u;
+                    unsigned long long v = sw ? ((unsigned long long)(Store::size_m1(to) + 1) |
+                                                 ((unsigned long long)(so & 1u) << 40) |
+                                                 ((unsigned long long)(so >> 1) << 50)) : 0ull;
+                    unsigned long long incl = v;
+#pragma unroll
+                    for (int k = 1; k < 32; k <<= 1) {
+                        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, k);
+                        if (lane >= k) incl += t;
+                    }
+                    if (lane == 31) sh->scan_tot[warp] = incl;
+                    __syncthreads();
+                    unsigned long long pre = incl - v, total = 0;
+#pragma unroll
+                    for (int w = 0; w < CTA_WARPS; ++w) {
+                        const unsigned long long t = sh->scan_tot[w];
+                        if (w < warp) pre += t;
+                        total += t;
+                    }
+                    if (sw) {
+                        const uint32_t hub_m1 = Store::size_m1(th);     // hub size - 1 at round start
+                        const uint32_t pre_sz = (uint32_t)(pre & 0xffffffffffull);
+                        rec = make_rec<Rec>(Store::size_m1(to), hub_m1 + pre_sz);
+                        st.make_child(o, hub);
+                        if (track) {
+                            const uint32_t hs = st.sides_of_root(hub, th);
+                            const unsigned long long in = pre + v;
+                            const uint32_t m = hs | (((in >> 40) & 0x3ffu) ? 1u : 0u) |
+                                               (((in >> 50) & 0x3ffu) ? 2u : 0u);
+                            if (m == 3u || a.any3) atomicMin(&sh->span_min, (uint32_t)n + 1);
+                        }
+                        if (pre_sz == 0) {      // first star bond of the round: publish the hub
+                            const uint32_t tot_sz = (uint32_t)(total & 0xffffffffffull);
+                            const uint32_t add = (((total >> 40) & 0x3ffu) ? 1u : 0u) |
+                                                 (((total >> 50) & 0x3ffu) ? 2u : 0u);
+                            st.set_root(hub, hub_m1 + tot_sz, track ? add : 0u);
+                            atomicMax(&sh->hub_key,
+                                      ((unsigned long long)(hub_m1 + tot_sz + 1) << 32) | hub);
+                        }
+                        won = true;
+                    }
+                }
+                if (won) pending = false;
+                --epoch;
+                if (tid == 0) sh->bmin = 0xffffffffu;           // read only between the two barriers above
+                if (!__syncthreads_or(pending)) break;          // every candidate merged
+                if (pending) {                                  // walk up to the new roots
+                    st.find2(ru, rv, tu, tv);
+                    pending = ru != rv;
                 }
             }
-        } else {
-            // ---------------- merger ----------------
-            Rec *rec_out = reinterpret_cast<Rec *>(a.recs) + (size_t)run * M;
-            uint32_t nspan = NSPAN_NEVER;
-            bool track = spanning;
-            for (int b = 0; b < nb; ++b) {
-                const int slot = b % RING;
-                while (ld_volatile(&ready[slot]) != (uint32_t)b + 1) __nanosleep(20);
-                __threadfence_block();
-                const Edge pr = ld_pair(&ring[slot * 32 + lane]);
-                __syncwarp();
-                if (lane == 0) st_volatile(done, (uint32_t)b + 1);
-                const int n = b * 32 + lane;
-                const bool valid = n < M;
-                uint32_t ru = 0, rv = 0, tu = 0, tv = 0;
-                if (valid) {
-                    uint32_t x, y;
-                    edge_uv(pr, x, y);
-                    ru = st.find(x, tu);
-                    rv = st.find(y, tv);
-                }
-                uint32_t span_n;
-                const Rec rec = merge_batch(st, claim, clog, lane, valid, n, ru, tu, rv, tv, track,
-                                            a.any3, span_n);
-                if (track && span_n != NSPAN_NEVER) { nspan = span_n; track = false; }
-                if (valid) __stcs(&rec_out[n], rec);
-            }
-            if (lane == 0) a.nspan[run] = nspan;
+            if (track && sh->span_min != NSPAN_NEVER) track = false;
+            if (valid) __stcs(&rec_out[n], rec);
         }
+        __syncthreads();
+        if (tid == 0) a.nspan[run] = sh->span_min;
         __syncthreads();
     }
 }
@@ -485,27 +605,29 @@ __global__ void __launch_bounds__(TEAM_THREADS, 4) sweep_team_kernel(SweepArgs a
 // ---------------------------------------------------------------------------
 // planning and launch
 // ---------------------------------------------------------------------------
+
 static int ilog2_ceil(uint32_t x) { int l = 0; while ((1u << l) < x) ++l; return l; }
 
 static SweepPlan plan_team(SweepPlan p, int32_t N, int32_t R, int sms, size_t smem_optin,
                            size_t store_bytes)
 {
-    // one CTA of TEAM_THREADS per run; as many CTAs per SM as shared memory and
-    // the 64-warp limit allow
+    // one CTA of CTA_THREADS per run; as many CTAs per SM as shared memory and
+    // the 64-warp limit allow.  Claim table: exact (one slot per node) when it
+    // fits next to the store, else as large as fits (hashed).
     const size_t sm_total = 228 * 1024;
-    const size_t edge_bytes = p.kind == STORE_G32 ? 8 : 4;
-    int clog = p.claim_log2;
-    size_t fixed = store_bytes + edge_bytes * RING * 32 + 4 * (RING + 1) + 16;
+    const size_t fixed = store_bytes + 64;     // + CtaShared
+    int clog = ilog2_ceil((uint32_t)(N < 256 ? 256 : N));
+    if (clog > 14) clog = 14;
     while (clog > 8 && fixed + ((size_t)4 << clog) > smem_optin) --clog;
     p.claim_log2 = clog;
     p.team = 1;
     p.store_bytes = store_bytes;
-    p.warps_per_cta = TEAM_FINDERS + 1;
+    p.warps_per_cta = CTA_WARPS;
     p.smem_bytes = align16h(fixed + ((size_t)4 << clog));
     p.slice_bytes = p.smem_bytes;
     int ctas_per_sm = (int)(sm_total / (p.smem_bytes + 1024));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
-    if (ctas_per_sm > 64 / (TEAM_FINDERS + 1)) ctas_per_sm = 64 / (TEAM_FINDERS + 1);
+    if (ctas_per_sm > 64 / CTA_WARPS) ctas_per_sm = 64 / CTA_WARPS;
     if (p.kind == STORE_G32 && ctas_per_sm > 4) ctas_per_sm = 4;
     long long grid = (long long)sms * ctas_per_sm;
     if (grid > R) grid = R;
@@ -571,11 +693,11 @@ SweepPlan plan_sweep(int32_t N, int32_t R, int sms, size_t smem_optin, int force
 template <class Store>
 static cudaError_t launch_team_t(const SweepPlan &p, const SweepArgs &a, cudaStream_t s)
 {
-    cudaError_t e = cudaFuncSetAttribute(sweep_team_kernel<Store>,
+    cudaError_t e = cudaFuncSetAttribute(sweep_cta_kernel<Store>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)p.smem_bytes);
     if (e != cudaSuccess) return e;
-    sweep_team_kernel<Store><<<p.grid, TEAM_THREADS, p.smem_bytes, s>>>(a, (uint32_t)p.store_bytes);
+    sweep_cta_kernel<Store><<<p.grid, CTA_THREADS, p.smem_bytes, s>>>(a, (uint32_t)p.store_bytes);
     return cudaGetLastError();
 }
 
