@@ -50,8 +50,10 @@ struct pz_ctx {
     int sms = 0;
     size_t smem_optin = 0;
     int force_kind = -1;
-    int team = 1;             // finder/merger team kernel (PZ_SWEEP_TEAM=0: single-warp kernel)
-    size_t chunk_bytes = (size_t)8 << 30;
+    int team = 1;             // CTA lock-step kernel (PZ_SWEEP_TEAM=0: single-warp A/B kernel)
+    int claim_cap = 0;        // log2 of the largest claim table (PZ_CLAIM_LOG2; 0 = automatic)
+    int cta_warps = 0;        // warps of a sweep CTA = bonds per batch / 32 (PZ_CTA_WARPS; 0 = automatic)
+    size_t chunk_bytes = (size_t)24 << 30;      // total scratch budget of the slots
 
     // graph
     int32_t N = 0, M = 0;
@@ -61,21 +63,36 @@ struct pz_ctx {
     DevBuf<uint2> edges64;
     DevBuf<uint32_t> sides2;
 
-    // per-chunk scratch
-    DevBuf<int32_t> perms;
-    DevBuf<unsigned char> recs;
-    DevBuf<uint32_t> nspan;
+    // per-chunk scratch: PZ_SLOTS chunks of runs are in flight at once
+    // (bond orders of chunk c+1 and statistics of chunk c-1 overlap the sweep
+    // of chunk c on separate streams)
+    struct Slot {
+        DevBuf<int32_t> perms;
+        DevBuf<unsigned char> recs;
+        DevBuf<uint32_t> nspan;
+        DevBuf<uint32_t> seeds;
+        DevBuf<RunState> ckpt;
+        DevBuf<double> canon_runs;        // [R][num_p][7]
+        DevBuf<double> canon_red;         // 2 * num_p * 7 (mean, M2 of the chunk)
+        double *red_host = nullptr;        // pinned, 2 * num_p * 7
+        size_t red_host_cap = 0;
+        cudaEvent_t perm_done = nullptr, sweep_done = nullptr, stats_done = nullptr;
+        int32_t runs = 0;                 // runs of the chunk whose result is not yet merged
+        bool canon_pending = false;
+    };
+    static constexpr int PZ_SLOTS = 3;
+    Slot slots[PZ_SLOTS];
+    cudaStream_t s_perm = nullptr, s_stats = nullptr;
+    int pipeline = 1;                     // PZ_PIPELINE=0: everything on one stream
     DevBuf<uint32_t> gscratch;
     DevBuf<uint8_t> rows;
-    DevBuf<uint32_t> seeds;
 
     // micro accumulators
     DevBuf<unsigned long long> acc;       // (M+1) * PZ_ACC_WORDS
     DevBuf<unsigned long long> span_cum;  // M + 1
     DevBuf<double> fin;                   // 13 * (M+1): mean[7], var[6]
     int64_t micro_runs = 0;
-    DevBuf<RunState> ckpt;                // [R][n_ckpt] run state every ckpt_every rows
-    int ckpt_every = 1024;
+    int ckpt_every = 1024;                // run state checkpoints every so many rows
 
     // canonical
     int32_t num_p = 0;
@@ -87,8 +104,7 @@ struct pz_ctx {
     DevBuf<int32_t> band_lo, band_hi, porder_dev;
     DevBuf<double> cols;                  // scratch of the contraction
     DevBuf<double> cols_out;
-    DevBuf<double> canon_red;             // 2 * num_p * 7
-    DevBuf<double> canon_runs;            // [R][num_p][7] of the last fused call
+    const double *canon_last_ptr = nullptr;   // per-run values of the last chunk of the last fused call
     int32_t canon_last_R = 0;
     int64_t canon_count = 0;
     std::vector<double> canon_mean, canon_m2;
@@ -105,15 +121,16 @@ struct pz_ctx {
 };
 
 struct PhaseTimer {
-    pz_ctx *c; int phase; cudaEvent_t a = nullptr, b = nullptr;
-    PhaseTimer(pz_ctx *c_, int phase_) : c(c_), phase(phase_) {
+    pz_ctx *c; int phase; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
+    PhaseTimer(pz_ctx *c_, int phase_, cudaStream_t st_ = nullptr)
+        : c(c_), phase(phase_), st(st_ ? st_ : c_->stream) {
         if (!c->profiling) return;
         cudaEventCreate(&a); cudaEventCreate(&b);
-        cudaEventRecord(a, c->stream);
+        cudaEventRecord(a, st);
     }
     ~PhaseTimer() {
         if (!c->profiling) return;
-        cudaEventRecord(b, c->stream);
+        cudaEventRecord(b, st);
         c->pending.push_back({phase, {a, b}});
     }
 };
@@ -180,8 +197,18 @@ int pz_create(int device, pz_ctx **out)
     c->sms = prop.multiProcessorCount;
     c->smem_optin = prop.sharedMemPerBlockOptin;
     PZ_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    PZ_CUDA(cudaStreamCreateWithFlags(&c->s_perm, cudaStreamNonBlocking));
+    PZ_CUDA(cudaStreamCreateWithFlags(&c->s_stats, cudaStreamNonBlocking));
+    for (auto &sl : c->slots) {
+        PZ_CUDA(cudaEventCreateWithFlags(&sl.perm_done, cudaEventDisableTiming));
+        PZ_CUDA(cudaEventCreateWithFlags(&sl.sweep_done, cudaEventDisableTiming));
+        PZ_CUDA(cudaEventCreateWithFlags(&sl.stats_done, cudaEventDisableTiming));
+    }
+    if (const char *e = getenv("PZ_PIPELINE")) c->pipeline = atoi(e);
     if (const char *e = getenv("PZ_FORCE_STORE")) c->force_kind = atoi(e);
     if (const char *e = getenv("PZ_SWEEP_TEAM")) c->team = atoi(e);
+    if (const char *e = getenv("PZ_CLAIM_LOG2")) c->claim_cap = atoi(e);
+    if (const char *e = getenv("PZ_CTA_WARPS")) c->cta_warps = atoi(e);
     if (const char *e = getenv("PZ_CHUNK_BYTES")) c->chunk_bytes = (size_t)atoll(e);
     *out = c;
     return PZ_OK;
@@ -191,13 +218,23 @@ void pz_destroy(pz_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    cudaDeviceSynchronize();
     c->edges32.release(); c->edges64.release(); c->sides2.release();
-    c->perms.release(); c->recs.release(); c->nspan.release(); c->gscratch.release();
-    c->rows.release(); c->seeds.release(); c->acc.release(); c->span_cum.release();
-    c->fin.release(); c->ckpt.release(); c->ps_dev.release(); c->band_lo.release();
+    for (auto &sl : c->slots) {
+        sl.perms.release(); sl.recs.release(); sl.nspan.release(); sl.seeds.release();
+        sl.ckpt.release(); sl.canon_runs.release(); sl.canon_red.release();
+        if (sl.red_host) cudaFreeHost(sl.red_host);
+        if (sl.perm_done) cudaEventDestroy(sl.perm_done);
+        if (sl.sweep_done) cudaEventDestroy(sl.sweep_done);
+        if (sl.stats_done) cudaEventDestroy(sl.stats_done);
+    }
+    c->gscratch.release(); c->rows.release(); c->acc.release(); c->span_cum.release();
+    c->fin.release(); c->ps_dev.release(); c->band_lo.release();
     c->band_hi.release(); c->porder_dev.release(); c->cols.release(); c->cols_out.release();
-    c->canon_red.release(); c->pmf.release(); c->canon_runs.release();
+    c->pmf.release();
+    if (c->timer_a) { cudaEventDestroy(c->timer_a); cudaEventDestroy(c->timer_b); }
+    cudaStreamDestroy(c->s_perm);
+    cudaStreamDestroy(c->s_stats);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -210,7 +247,9 @@ int pz_synchronize(pz_ctx *c)
 {
     if (!c) return fail(PZ_ERR_ARG, "null context");
     PZ_CUDA(cudaSetDevice(c->device));
+    PZ_CUDA(cudaStreamSynchronize(c->s_perm));
     PZ_CUDA(cudaStreamSynchronize(c->stream));
+    PZ_CUDA(cudaStreamSynchronize(c->s_stats));
     return PZ_OK;
 }
 
@@ -278,8 +317,10 @@ struct Chunk {
     const int32_t *perms_dev;
 };
 
-static int sweep_chunk(pz_ctx *c, int32_t R, int perm_mode_in, const void *perm_src, size_t run0,
-                       Chunk *out)
+// bond orders of the chunk on `sp` (slot buffers), then the sweep on the
+// context's main stream; `sl.sweep_done` is recorded behind the sweep
+static int sweep_chunk(pz_ctx *c, pz_ctx::Slot &sl, cudaStream_t sp, int32_t R, int perm_mode_in,
+                       const void *perm_src, size_t run0, Chunk *out)
 {
     const int32_t M = c->M;
     const bool seeds_on_device = (perm_mode_in & PZ_SEEDS_ON_DEVICE) != 0;
@@ -289,36 +330,40 @@ static int sweep_chunk(pz_ctx *c, int32_t R, int perm_mode_in, const void *perm_
     if (perm_mode == PZ_PERM_DEVICE) {
         perms_dev = (const int32_t *)perm_src + run0 * (size_t)M;
     } else {
-        PZ_CUDA(c->perms.ensure(pm));
-        perms_dev = c->perms.p;
+        PZ_CUDA(sl.perms.ensure(pm));
+        perms_dev = sl.perms.p;
         if (perm_mode == PZ_PERM_HOST) {
             if (M > 0)
-                PZ_CUDA(cudaMemcpyAsync(c->perms.p, (const int32_t *)perm_src + run0 * (size_t)M,
-                                        (size_t)R * M * 4, cudaMemcpyHostToDevice, c->stream));
+                PZ_CUDA(cudaMemcpyAsync(sl.perms.p, (const int32_t *)perm_src + run0 * (size_t)M,
+                                        (size_t)R * M * 4, cudaMemcpyHostToDevice, sp));
         } else {
             const uint32_t *seeds_dev = (const uint32_t *)perm_src + run0;
             if (!seeds_on_device) {
-                PZ_CUDA(c->seeds.ensure((size_t)R));
-                PZ_CUDA(cudaMemcpyAsync(c->seeds.p, (const uint32_t *)perm_src + run0, (size_t)R * 4,
-                                        cudaMemcpyHostToDevice, c->stream));
-                seeds_dev = c->seeds.p;
+                PZ_CUDA(sl.seeds.ensure((size_t)R));
+                PZ_CUDA(cudaMemcpyAsync(sl.seeds.p, (const uint32_t *)perm_src + run0, (size_t)R * 4,
+                                        cudaMemcpyHostToDevice, sp));
+                seeds_dev = sl.seeds.p;
             }
             int l = 0;
-            PhaseTimer t(c, PZ_PHASE_PERM);
+            PhaseTimer t(c, PZ_PHASE_PERM, sp);
             if (perm_mode == PZ_PERM_PHILOX)
-                PZ_CUDA(launch_perm_philox(M, R, seeds_dev, c->perms.p, c->stream, &l));
+                PZ_CUDA(launch_perm_philox(M, R, seeds_dev, sl.perms.p, sp, &l));
             else
-                PZ_CUDA(launch_perm_mt19937(M, R, seeds_dev, c->perms.p, c->stream, &l));
+                PZ_CUDA(launch_perm_mt19937(M, R, seeds_dev, sl.perms.p, sp, &l));
             c->launches += l;
         }
     }
-    SweepPlan plan = plan_sweep(c->N, R, c->sms, c->smem_optin, c->force_kind, c->team);
+    SweepPlan plan = plan_sweep(c->N, R, c->sms, c->smem_optin, c->force_kind, c->team, c->claim_cap, c->cta_warps);
     if (plan.kind != STORE_G32 && c->N > 65536)
         return fail(PZ_ERR_ARG, "forced shared-memory store needs N <= 65536");
     const bool rec64 = plan.kind == STORE_G32;
-    PZ_CUDA(c->recs.ensure(pm * (rec64 ? 8 : 4)));
-    PZ_CUDA(c->nspan.ensure((size_t)R));
+    PZ_CUDA(sl.recs.ensure(pm * (rec64 ? 8 : 4)));
+    PZ_CUDA(sl.nspan.ensure((size_t)R));
     if (plan.gscratch_bytes) PZ_CUDA(c->gscratch.ensure(plan.gscratch_bytes / 4));
+    if (sp != c->stream) {
+        PZ_CUDA(cudaEventRecord(sl.perm_done, sp));
+        PZ_CUDA(cudaStreamWaitEvent(c->stream, sl.perm_done, 0));
+    }
 
     SweepArgs sa{};
     sa.N = c->N; sa.M = M; sa.R = R;
@@ -326,8 +371,8 @@ static int sweep_chunk(pz_ctx *c, int32_t R, int perm_mode_in, const void *perm_
     sa.sides2 = c->spanning ? c->sides2.p : nullptr;
     sa.any3 = c->any3;
     sa.perms = perms_dev;
-    sa.recs = c->recs.p;
-    sa.nspan = c->nspan.p;
+    sa.recs = sl.recs.p;
+    sa.nspan = sl.nspan.p;
     sa.gscratch = c->gscratch.p;
     sa.claim_log2 = plan.claim_log2;
     {
@@ -335,10 +380,11 @@ static int sweep_chunk(pz_ctx *c, int32_t R, int perm_mode_in, const void *perm_
         PZ_CUDA(launch_sweep(plan, sa, c->stream));
     }
     c->launches += 1;
+    PZ_CUDA(cudaEventRecord(sl.sweep_done, c->stream));
 
     out->plan = plan;
     out->perms_dev = perms_dev;
-    out->stats = StatsArgs{c->N, M, R, rec64 ? 1 : 0, c->recs.p, c->nspan.p, perms_dev,
+    out->stats = StatsArgs{c->N, M, R, rec64 ? 1 : 0, sl.recs.p, sl.nspan.p, perms_dev,
                            c->spanning ? 1 : 0};
     return PZ_OK;
 }
@@ -368,11 +414,11 @@ int pz_run_rows(pz_ctx *c, int32_t R, int perm_mode, const void *perm_src, void 
     PZ_CUDA(cudaSetDevice(c->device));
     const size_t rb = c->spanning ? 53 : 52;
     const size_t run_bytes = ((size_t)c->M + 1) * rb;
-    size_t chunk = std::max<size_t>(1, c->chunk_bytes / run_bytes);
+    size_t chunk = std::max<size_t>(1, (c->chunk_bytes / pz_ctx::PZ_SLOTS) / (run_bytes + 8 * (size_t)c->M));
     for (size_t r0 = 0; r0 < (size_t)R; r0 += chunk) {
         const int32_t rc_n = (int32_t)std::min(chunk, (size_t)R - r0);
         Chunk ch;
-        rc = sweep_chunk(c, rc_n, perm_mode, perm_src, r0, &ch);
+        rc = sweep_chunk(c, c->slots[0], c->stream, rc_n, perm_mode, perm_src, r0, &ch);
         if (rc) return rc;
         PZ_CUDA(c->rows.ensure((size_t)rc_n * run_bytes));
         {
@@ -441,18 +487,20 @@ int pz_make_perms(pz_ctx *c, int32_t R, int perm_mode, const uint32_t *seeds, in
     if (R == 0 || c->M == 0) return PZ_OK;
     PZ_CUDA(cudaSetDevice(c->device));
     const size_t per_run = (size_t)c->M * 4;
-    const size_t chunk = is_device ? (size_t)R : std::max<size_t>(1, c->chunk_bytes / per_run);
+    const size_t chunk = is_device ? (size_t)R
+                                   : std::max<size_t>(1, (c->chunk_bytes / pz_ctx::PZ_SLOTS) / per_run);
     for (size_t r0 = 0; r0 < (size_t)R; r0 += chunk) {
         const int32_t n = (int32_t)std::min(chunk, (size_t)R - r0);
-        PZ_CUDA(c->seeds.ensure((size_t)n));
-        PZ_CUDA(cudaMemcpyAsync(c->seeds.p, seeds + r0, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+        pz_ctx::Slot &sl = c->slots[0];
+        PZ_CUDA(sl.seeds.ensure((size_t)n));
+        PZ_CUDA(cudaMemcpyAsync(sl.seeds.p, seeds + r0, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
         int32_t *dst = out + r0 * (size_t)c->M;
-        if (!is_device) { PZ_CUDA(c->perms.ensure((size_t)n * c->M)); dst = c->perms.p; }
+        if (!is_device) { PZ_CUDA(sl.perms.ensure((size_t)n * c->M)); dst = sl.perms.p; }
         int l = 0;
         {
             PhaseTimer t(c, PZ_PHASE_PERM);
-            if (perm_mode == PZ_PERM_PHILOX) PZ_CUDA(launch_perm_philox(c->M, n, c->seeds.p, dst, c->stream, &l));
-            else PZ_CUDA(launch_perm_mt19937(c->M, n, c->seeds.p, dst, c->stream, &l));
+            if (perm_mode == PZ_PERM_PHILOX) PZ_CUDA(launch_perm_philox(c->M, n, sl.seeds.p, dst, c->stream, &l));
+            else PZ_CUDA(launch_perm_mt19937(c->M, n, sl.seeds.p, dst, c->stream, &l));
         }
         c->launches += l;
         if (!is_device)
@@ -476,6 +524,20 @@ int pz_reset_accumulators(pz_ctx *c)
     return PZ_OK;
 }
 
+// fold the (mean, M2) of a finished chunk into the context (chunks are
+// harvested in submission order, so the result does not depend on timing)
+static int harvest_slot(pz_ctx *c, pz_ctx::Slot &sl)
+{
+    if (!sl.canon_pending) return PZ_OK;
+    PZ_CUDA(cudaEventSynchronize(sl.stats_done));
+    const size_t cols = (size_t)c->num_p * PZ_CANON_COLS;
+    c->canon_mean.resize(cols); c->canon_m2.resize(cols);
+    chan_merge(c->canon_count, c->canon_mean, c->canon_m2, sl.runs, sl.red_host,
+               sl.red_host + cols);
+    sl.canon_pending = false;
+    return PZ_OK;
+}
+
 int pz_run_fused(pz_ctx *c, int32_t R, int perm_mode, const void *perm_src, int flags)
 {
     int rc = check_run_args(c, R, perm_mode, perm_src);
@@ -485,54 +547,85 @@ int pz_run_fused(pz_ctx *c, int32_t R, int perm_mode, const void *perm_src, int 
         return fail(PZ_ERR_STATE, "pz_run_fused: PZ_FUSE_CANON needs pz_set_ps(M = bonds of the graph) first");
     PZ_CUDA(cudaSetDevice(c->device));
     if (flags & PZ_FUSE_MICRO) { rc = ensure_acc(c); if (rc) return rc; }
+    // everything issued so far on the main stream (graph, weights, resets) must
+    // be visible to the side streams
+    PZ_CUDA(cudaStreamSynchronize(c->stream));
     const int P = c->num_p;
-    const size_t per_run = (size_t)std::max(c->M, 1) * 12;       // perms + widest records
-    const size_t chunk = std::max<size_t>(1, c->chunk_bytes / per_run);
+    const int nslot = c->pipeline ? pz_ctx::PZ_SLOTS : 1;
+    const size_t per_run = (size_t)std::max(c->M, 1) * 12 + 4096;   // orders + widest records + checkpoints
+    size_t chunk = std::max<size_t>(1, (c->chunk_bytes / pz_ctx::PZ_SLOTS) / per_run);
+    // at least a few chunks so that the streams overlap, but never below 4 waves of runs
+    if (nslot > 1) {
+        const size_t want = std::max<size_t>((size_t)c->sms * 4, ((size_t)R + 2 * nslot - 1) / (2 * nslot));
+        chunk = std::min(chunk, want);
+    }
     const int n_ckpt = c->M / c->ckpt_every + 1;
-    for (size_t r0 = 0; r0 < (size_t)R; r0 += chunk) {
+    cudaStream_t sp = c->pipeline ? c->s_perm : c->stream;
+    cudaStream_t ss = c->pipeline ? c->s_stats : c->stream;
+    size_t ci = 0;
+    for (size_t r0 = 0; r0 < (size_t)R; r0 += chunk, ++ci) {
         const int32_t n = (int32_t)std::min(chunk, (size_t)R - r0);
+        pz_ctx::Slot &sl = c->slots[ci % nslot];
+        // the slot's previous chunk must be done before its buffers are reused
+        if (ci >= (size_t)nslot) {
+            rc = harvest_slot(c, sl); if (rc) return rc;
+            PZ_CUDA(cudaEventSynchronize(sl.stats_done));
+        }
         Chunk ch;
-        rc = sweep_chunk(c, n, perm_mode, perm_src, r0, &ch);
+        rc = sweep_chunk(c, sl, sp, n, perm_mode, perm_src, r0, &ch);
         if (rc) return rc;
-        PZ_CUDA(c->ckpt.ensure((size_t)n * n_ckpt));
-        RunState *ck = c->ckpt.p;
+        PZ_CUDA(sl.ckpt.ensure((size_t)n * n_ckpt));
+        if (ss != c->stream) PZ_CUDA(cudaStreamWaitEvent(ss, sl.sweep_done, 0));
         {
-            PhaseTimer t(c, PZ_PHASE_CKPT);
-            PZ_CUDA(launch_checkpoints(ch.stats, ck, c->ckpt_every, n_ckpt, c->stream));
+            PhaseTimer t(c, PZ_PHASE_CKPT, ss);
+            PZ_CUDA(launch_checkpoints(ch.stats, sl.ckpt.p, c->ckpt_every, n_ckpt, ss));
         }
         c->launches += 1;
         if (flags & PZ_FUSE_MICRO) {
-            PhaseTimer t(c, PZ_PHASE_ACCUM);
-            PZ_CUDA(launch_accumulate(ch.stats, c->acc.p, ck, c->ckpt_every, n_ckpt, c->stream));
+            PhaseTimer t(c, PZ_PHASE_ACCUM, ss);
+            PZ_CUDA(launch_accumulate(ch.stats, c->acc.p, sl.ckpt.p, c->ckpt_every, n_ckpt, ss));
             c->launches += 1;
             c->micro_runs += n;
         }
         if (flags & PZ_FUSE_CANON) {
             const int cols = P * PZ_CANON_COLS;
-            PZ_CUDA(c->canon_runs.ensure((size_t)n * cols));
-            PZ_CUDA(c->canon_red.ensure((size_t)2 * cols));
+            PZ_CUDA(sl.canon_runs.ensure((size_t)n * cols));
+            PZ_CUDA(sl.canon_red.ensure((size_t)2 * cols));
             {
-                PhaseTimer t(c, PZ_PHASE_CANON);
+                PhaseTimer t(c, PZ_PHASE_CANON, ss);
                 PZ_CUDA(launch_canon_runs(ch.stats, P, c->pmf.p, c->band_lo.p, c->band_hi.p,
-                                          c->porder_dev.p, ck, c->ckpt_every, n_ckpt,
-                                          c->canon_runs.p, c->stream));
+                                          c->porder_dev.p, sl.ckpt.p, c->ckpt_every, n_ckpt,
+                                          sl.canon_runs.p, ss));
             }
             {
-                PhaseTimer t(c, PZ_PHASE_REDUCE);
-                PZ_CUDA(launch_canon_reduce(n, cols, c->canon_runs.p, c->canon_red.p,
-                                            c->canon_red.p + cols, c->stream));
+                PhaseTimer t(c, PZ_PHASE_REDUCE, ss);
+                PZ_CUDA(launch_canon_reduce(n, cols, sl.canon_runs.p, sl.canon_red.p,
+                                            sl.canon_red.p + cols, ss));
             }
             c->launches += 2;
-            std::vector<double> red((size_t)2 * cols);
-            PZ_CUDA(cudaMemcpyAsync(red.data(), c->canon_red.p, red.size() * 8,
-                                    cudaMemcpyDeviceToHost, c->stream));
-            PZ_CUDA(cudaStreamSynchronize(c->stream));
-            c->canon_mean.resize(cols); c->canon_m2.resize(cols);
-            chan_merge(c->canon_count, c->canon_mean, c->canon_m2, n, red.data(), red.data() + cols);
+            if (sl.red_host_cap < (size_t)2 * cols) {
+                if (sl.red_host) cudaFreeHost(sl.red_host);
+                sl.red_host = nullptr; sl.red_host_cap = 0;
+                PZ_CUDA(cudaMallocHost(&sl.red_host, (size_t)2 * cols * 8));
+                sl.red_host_cap = (size_t)2 * cols;
+            }
+            PZ_CUDA(cudaMemcpyAsync(sl.red_host, sl.canon_red.p, (size_t)2 * cols * 8,
+                                    cudaMemcpyDeviceToHost, ss));
+            sl.runs = n;
+            sl.canon_pending = true;
             c->canon_last_R = n;
+            c->canon_last_ptr = sl.canon_runs.p;
         }
-        if (c->profiling) collect_phases(c);
+        PZ_CUDA(cudaEventRecord(sl.stats_done, ss));
     }
+    // drain: harvest the remaining chunks in submission order
+    for (size_t k = (ci > (size_t)nslot ? ci - nslot : 0); k < ci; ++k) {
+        rc = harvest_slot(c, c->slots[k % nslot]); if (rc) return rc;
+    }
+    PZ_CUDA(cudaStreamSynchronize(sp));
+    PZ_CUDA(cudaStreamSynchronize(c->stream));
+    PZ_CUDA(cudaStreamSynchronize(ss));
+    if (c->profiling) collect_phases(c);
     return PZ_OK;
 }
 
@@ -697,7 +790,7 @@ int pz_canon_last_runs(pz_ctx *c, double *out)
     if (!c || !out) return fail(PZ_ERR_ARG, "pz_canon_last_runs: bad arguments");
     if (c->canon_last_R == 0) return fail(PZ_ERR_STATE, "pz_canon_last_runs: no fused canonical batch yet");
     PZ_CUDA(cudaSetDevice(c->device));
-    PZ_CUDA(cudaMemcpyAsync(out, c->canon_runs.p,
+    PZ_CUDA(cudaMemcpyAsync(out, c->canon_last_ptr,
                             (size_t)c->canon_last_R * c->num_p * PZ_CANON_COLS * 8,
                             cudaMemcpyDeviceToHost, c->stream));
     PZ_CUDA(cudaStreamSynchronize(c->stream));

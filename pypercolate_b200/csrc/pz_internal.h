@@ -38,7 +38,8 @@ struct SweepPlan {
 
 // choose store, CTA shape and grid for a graph of N nodes on a device with
 // `sms` SMs and `smem_optin` bytes of opt-in shared memory per CTA
-SweepPlan plan_sweep(int32_t N, int32_t R, int sms, size_t smem_optin, int force_kind, int team);
+SweepPlan plan_sweep(int32_t N, int32_t R, int sms, size_t smem_optin, int force_kind, int team,
+                     int claim_cap_log2, int cta_warps);
 cudaError_t launch_sweep(const SweepPlan &plan, const SweepArgs &args, cudaStream_t stream);
 
 // ---- statistics kernels (pz_stats.cu) ---------------------------------------

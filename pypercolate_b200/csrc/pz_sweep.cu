@@ -444,19 +444,19 @@ __global__ void sweep_kernel(SweepArgs a, uint32_t slice_bytes)
 // the same run, and every dependent-latency chain (find, claim, merge) is paid
 // once per CTA_THREADS bonds instead of once per 32.
 // ---------------------------------------------------------------------------
-static constexpr int CTA_WARPS = 4;
-static constexpr int CTA_THREADS = 32 * CTA_WARPS;
+static constexpr int CTA_MAX_WARPS = 16;
 
 struct CtaShared {
     unsigned long long hub_key;               // (size << 32) | root of the largest cluster seen
-    unsigned long long scan_tot[CTA_WARPS];
+    unsigned long long scan_tot[CTA_MAX_WARPS];
     uint32_t span_min;
     uint32_t bmin;                            // lowest blocked position of the round
 };
 
-template <class Store>
-__global__ void __launch_bounds__(CTA_THREADS, 4) sweep_cta_kernel(SweepArgs a, uint32_t store_bytes)
+template <class Store, int CTA_WARPS>
+__global__ void __launch_bounds__(32 * CTA_WARPS, 1) sweep_cta_kernel(SweepArgs a, uint32_t store_bytes)
 {
+    constexpr int CTA_THREADS = 32 * CTA_WARPS;
     extern __shared__ __align__(16) unsigned char smem[];
     using Rec = typename Store::Rec;
     using Edge = typename Store::Edge;
@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) sweep_cta_kernel(SweepArgs a, 
         const int32_t *perm = a.perms + (size_t)run * M;
         Rec *rec_out = reinterpret_cast<Rec *>(a.recs) + (size_t)run * M;
         bool track = spanning;                 // CTA-uniform
-        uint32_t epoch = 0x00ffffffu;          // decreasing: newer claims always win over stale ones
+        uint32_t epoch = 0x003fffffu;          // decreasing: newer claims always win over stale ones
 
         // two-deep software pipeline: perm[n] -> edges[perm[n]] -> use
         Edge uv_next = Edge();
@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) sweep_cta_kernel(SweepArgs a, 
             bool pending = valid && ru != rv;
             Rec rec = 0;
             for (;;) {
-                const uint32_t key = (epoch << 8) | (uint32_t)tid;
+                const uint32_t key = (epoch << 10) | (uint32_t)tid;
                 const uint32_t hub = (uint32_t)sh->hub_key;
                 // star bond: one side is the hub; o = the other root
                 const bool star = pending && (ru == hub || rv == hub);
@@ -609,15 +609,18 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) sweep_cta_kernel(SweepArgs a, 
 static int ilog2_ceil(uint32_t x) { int l = 0; while ((1u << l) < x) ++l; return l; }
 
 static SweepPlan plan_team(SweepPlan p, int32_t N, int32_t R, int sms, size_t smem_optin,
-                           size_t store_bytes)
+                           size_t store_bytes, int claim_cap, int cta_warps)
 {
     // one CTA of CTA_THREADS per run; as many CTAs per SM as shared memory and
     // the 64-warp limit allow.  Claim table: exact (one slot per node) when it
     // fits next to the store, else as large as fits (hashed).
     const size_t sm_total = 228 * 1024;
-    const size_t fixed = store_bytes + 64;     // + CtaShared
+    const size_t fixed = store_bytes + 192;    // + CtaShared
+    const int CTA_WARPS = cta_warps;
     int clog = ilog2_ceil((uint32_t)(N < 256 ? 256 : N));
-    if (clog > 14) clog = 14;
+    if (claim_cap < 8) claim_cap = 8;
+    if (claim_cap > 14) claim_cap = 14;
+    if (clog > claim_cap) clog = claim_cap;
     while (clog > 8 && fixed + ((size_t)4 << clog) > smem_optin) --clog;
     p.claim_log2 = clog;
     p.team = 1;
@@ -637,7 +640,8 @@ static SweepPlan plan_team(SweepPlan p, int32_t N, int32_t R, int sms, size_t sm
     return p;
 }
 
-SweepPlan plan_sweep(int32_t N, int32_t R, int sms, size_t smem_optin, int force_kind, int team)
+SweepPlan plan_sweep(int32_t N, int32_t R, int sms, size_t smem_optin, int force_kind, int team,
+                     int claim_cap, int cta_warps)
 {
     SweepPlan p{};
     const size_t budget = smem_optin;          // per CTA (opt-in maximum)
@@ -656,7 +660,21 @@ SweepPlan plan_sweep(int32_t N, int32_t R, int sms, size_t smem_optin, int force
     if (clog > clog_max) clog = clog_max;
     while (clog > 8 && store_bytes + ((size_t)4 << clog) > budget) --clog;
     p.claim_log2 = clog;
-    if (team) return plan_team(p, N, R, sms, smem_optin, align16h(store_bytes));
+    if (team) {
+        // measured on B200 (profiles/sweep_cta_shape_r1.txt): when only one CTA fits an SM
+        // (L = 256) wide batches win (16 warps, largest claim table); when several fit, four
+        // warps per CTA and a 16 KB claim table keep more runs in flight
+        int w = cta_warps, cap = claim_cap;
+        if (w <= 0) {
+            const size_t sb = align16h(store_bytes);
+            const int fit = (int)((228 * 1024) / (sb + ((size_t)4 << 12) + 1024 + 192));
+            w = fit >= 4 ? 4 : fit >= 2 ? 8 : 16;
+            if (cap <= 0) cap = fit >= 2 ? 12 : 14;
+        }
+        if (cap <= 0) cap = 12;
+        w = w <= 2 ? 2 : w <= 4 ? 4 : w <= 8 ? 8 : 16;
+        return plan_team(p, N, R, sms, smem_optin, align16h(store_bytes), cap, w);
+    }
     p.slice_bytes = align16h(store_bytes + ((size_t)4 << clog));
 
     // warps (runs in flight) per CTA and CTAs per SM: as many runs as shared
@@ -690,15 +708,26 @@ SweepPlan plan_sweep(int32_t N, int32_t R, int sms, size_t smem_optin, int force
     return p;
 }
 
-template <class Store>
-static cudaError_t launch_team_t(const SweepPlan &p, const SweepArgs &a, cudaStream_t s)
+template <class Store, int W>
+static cudaError_t launch_team_w(const SweepPlan &p, const SweepArgs &a, cudaStream_t s)
 {
-    cudaError_t e = cudaFuncSetAttribute(sweep_cta_kernel<Store>,
+    cudaError_t e = cudaFuncSetAttribute(sweep_cta_kernel<Store, W>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)p.smem_bytes);
     if (e != cudaSuccess) return e;
-    sweep_cta_kernel<Store><<<p.grid, CTA_THREADS, p.smem_bytes, s>>>(a, (uint32_t)p.store_bytes);
+    sweep_cta_kernel<Store, W><<<p.grid, 32 * W, p.smem_bytes, s>>>(a, (uint32_t)p.store_bytes);
     return cudaGetLastError();
+}
+
+template <class Store>
+static cudaError_t launch_team_t(const SweepPlan &p, const SweepArgs &a, cudaStream_t s)
+{
+    switch (p.warps_per_cta) {
+    case 2: return launch_team_w<Store, 2>(p, a, s);
+    case 4: return launch_team_w<Store, 4>(p, a, s);
+    case 8: return launch_team_w<Store, 8>(p, a, s);
+    default: return launch_team_w<Store, 16>(p, a, s);
+    }
 }
 
 template <class Store>
