@@ -83,7 +83,7 @@ struct pz_ctx {
     static constexpr int PZ_SLOTS = 3;
     Slot slots[PZ_SLOTS];
     cudaStream_t s_perm = nullptr, s_stats = nullptr;
-    int pipeline = 1;                     // PZ_PIPELINE=0: everything on one stream
+    int pipeline = 0;                     // PZ_PIPELINE=1: bond orders / sweep / statistics on three streams
     DevBuf<uint32_t> gscratch;
     DevBuf<uint8_t> rows;
 

@@ -181,7 +181,7 @@ cudaError_t launch_canon_rows(int32_t M, int spanning, const uint8_t *rows, cons
 static constexpr int PC = 4;
 
 template <class RecT>
-__global__ void __launch_bounds__(128) canon_runs_kernel(StatsArgs a, int32_t P, int32_t nchunks,
+__global__ void __launch_bounds__(128, 4) canon_runs_kernel(StatsArgs a, int32_t P, int32_t nchunks,
                                                           const double *pmf, const int32_t *band_lo,
                                                           const int32_t *band_hi, const int32_t *porder,
                                                           const RunState *ckpt, int ckpt_every,
@@ -189,8 +189,10 @@ __global__ void __launch_bounds__(128) canon_runs_kernel(StatsArgs a, int32_t P,
 {
     constexpr int TILE = sizeof(RecT) == 4 ? 32 : 16;
     __shared__ RecT tile_all[4][32][TILE + 1];
+    __shared__ double ftile_all[4][PC][TILE];         // weights of the rows of the current tile
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     RecT (*tile)[TILE + 1] = tile_all[warp];
+    double (*ftile)[TILE] = ftile_all[warp];
     const long long wid = (long long)blockIdx.x * 4 + warp;
     const int rg = (int)(wid / nchunks), ch = (int)(wid % nchunks);
     const int run0 = rg * 32;
@@ -204,13 +206,9 @@ __global__ void __launch_bounds__(128) canon_runs_kernel(StatsArgs a, int32_t P,
     // chunk band (sorted-p order)
     const int p0 = ch * PC, np = min(PC, P - p0);
     int lo = M, hi = 0;
-    int plo[PC], phi[PC];
 #pragma unroll
-    for (int k = 0; k < PC; ++k) {
-        plo[k] = k < np ? band_lo[p0 + k] : M + 1;
-        phi[k] = k < np ? band_hi[p0 + k] : -1;
-        if (k < np) { lo = min(lo, plo[k]); hi = max(hi, phi[k]); }
-    }
+    for (int k = 0; k < PC; ++k)
+        if (k < np) { lo = min(lo, band_lo[p0 + k]); hi = max(hi, band_hi[p0 + k]); }
     const int ck = lo / ckpt_every;                 // checkpoint row = ck * ckpt_every <= lo
     const int row_start = ck * ckpt_every;          // state is the one AFTER this row
     RunState st;
@@ -226,7 +224,7 @@ __global__ void __launch_bounds__(128) canon_runs_kernel(StatsArgs a, int32_t P,
 
     double x[7];
     bool dirty = true;
-    auto contribute = [&](int n) {
+    auto refresh = [&](int n) {
         if (dirty) {
             uint64_t m[5];
             st.moments((uint32_t)a.N, m);
@@ -236,20 +234,21 @@ __global__ void __launch_bounds__(128) canon_runs_kernel(StatsArgs a, int32_t P,
             for (int k = 0; k < 5; ++k) x[2 + k] = (double)m[k];
             dirty = false;
         }
-#pragma unroll
-        for (int k = 0; k < PC; ++k) {
-            if (n >= plo[k] && n <= phi[k]) {
-                const double f = __ldg(&pmf[(size_t)(p0 + k) * S + n]);
-#pragma unroll
-                for (int q = 0; q < 7; ++q) acc[k][q] = fma(f, x[q], acc[k][q]);
-            }
-        }
     };
 
     // rows row_start .. hi; the state after row_start comes from the checkpoint,
-    // row n >= 1 applies record n-1
+    // row n >= 1 applies record n-1.  Inside the union band every weight is
+    // used: outside its own band a weight is exactly 0.0 and contributes nothing.
     int row = row_start;
-    if (row >= lo) contribute(row);
+    if (row >= lo) {
+        refresh(row);
+#pragma unroll
+        for (int k = 0; k < PC; ++k) {
+            const double f = __ldg(&pmf[(size_t)min(p0 + k, P - 1) * S + row]);
+#pragma unroll
+            for (int q = 0; q < 7; ++q) acc[k][q] = fma(f, x[q], acc[k][q]);
+        }
+    }
     while (row < hi) {
         __syncwarp();
         if (lane < TILE) {
@@ -259,6 +258,10 @@ __global__ void __launch_bounds__(128) canon_runs_kernel(StatsArgs a, int32_t P,
                 if (run0 + rr < a.R && idx < M) v = __ldg(&recs[(size_t)(run0 + rr) * M + idx]);
                 tile[rr][lane] = v;
             }
+#pragma unroll
+            for (int k = 0; k < PC; ++k)
+                ftile[k][lane] = (idx + 1 <= hi && idx + 1 >= lo)
+                                     ? __ldg(&pmf[(size_t)min(p0 + k, P - 1) * S + idx + 1]) : 0.0;
         }
         __syncwarp();
         const int cnt = min(TILE, hi - row);
@@ -270,7 +273,15 @@ __global__ void __launch_bounds__(128) canon_runs_kernel(StatsArgs a, int32_t P,
                 dirty = true;
             }
             if ((uint32_t)nrow == nspan) dirty = true;
-            if (nrow >= lo) contribute(nrow);
+            if (nrow >= lo) {
+                refresh(nrow);
+#pragma unroll
+                for (int k = 0; k < PC; ++k) {
+                    const double f = ftile[k][j];
+#pragma unroll
+                    for (int q = 0; q < 7; ++q) acc[k][q] = fma(f, x[q], acc[k][q]);
+                }
+            }
         }
         row += cnt;
     }

@@ -16,8 +16,10 @@
 //    uniformly and is placed by a STABLE counting sort (so the result does not
 //    depend on thread timing), then every bucket is shuffled by Fisher-Yates in
 //    shared memory with unbiased (Lemire) bounded draws.  One CTA per run.
-//    Counters: bucket draws (i >> 2, 0, 0, 0) lane i & 3; Fisher-Yates draws
-//    (step, bucket, attempt, 1).  Key: (seed, 0x50455243).
+//    Counters: bucket draws (i >> 2, 0, 0, 0) word i & 3; Fisher-Yates draw of
+//    step k of bucket b: word k & 3 of (k >> 2, b, 0, 1), on the (rare) Lemire
+//    rejection words 0.. of (k, b, attempt >= 1, 2).  Key: (seed, 0x50455243).
+//    Every Philox call therefore serves four bonds.
 //    oracle/pz_oracle.c restates this algorithm on the CPU for bit-exact tests.
 #include "pz_common.cuh"
 #include "pz_internal.h"
@@ -49,29 +51,34 @@ static constexpr uint32_t PHILOX_KEY1 = 0x50455243u;   // 'PERC'
 static constexpr int PH_THREADS = 256;
 static constexpr int PH_WARPS = PH_THREADS / 32;
 
-__device__ __forceinline__ uint32_t philox_bucket(uint32_t seed, uint32_t i, uint32_t bmask)
+// the four bucket words of bonds 4g .. 4g+3
+__device__ __forceinline__ void philox_buckets4(uint32_t seed, uint32_t g, uint32_t (&o)[4])
 {
-    uint32_t o[4];
-    philox4x32_10(seed, PHILOX_KEY1, i >> 2, 0u, 0u, 0u, o);
-    return o[i & 3u] & bmask;
+    philox4x32_10(seed, PHILOX_KEY1, g, 0u, 0u, 0u, o);
 }
 
-// unbiased j in [0, k] (Lemire), draws taken from counter (step, bucket, attempt, 1)
-__device__ __forceinline__ uint32_t philox_bounded(uint32_t seed, uint32_t step, uint32_t bucket,
-                                                   uint32_t k)
+// unbiased j in [0, k] (Lemire).  `o` caches the four words of counter
+// (k >> 2, bucket, 0, 1); `grp` is the group they belong to.
+__device__ __forceinline__ uint32_t philox_bounded(uint32_t seed, uint32_t bucket, uint32_t k,
+                                                   uint32_t (&o)[4], uint32_t &grp)
 {
     const uint32_t range = k + 1u;
+    if ((k >> 2) != grp) {
+        grp = k >> 2;
+        philox4x32_10(seed, PHILOX_KEY1, grp, bucket, 0u, 1u, o);
+    }
+    const uint32_t w = (k & 2u) ? ((k & 1u) ? o[3] : o[2]) : ((k & 1u) ? o[1] : o[0]);
+    uint64_t m = (uint64_t)w * range;
     const uint32_t thresh = (0u - range) % range;
-    uint32_t attempt = 0;
-    for (;;) {
-        uint32_t o[4];
-        philox4x32_10(seed, PHILOX_KEY1, step, bucket, attempt, 1u, o);
+    if ((uint32_t)m >= thresh) return (uint32_t)(m >> 32);
+    for (uint32_t attempt = 1;; ++attempt) {
+        uint32_t r[4];
+        philox4x32_10(seed, PHILOX_KEY1, k, bucket, attempt, 2u, r);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const uint64_t m = (uint64_t)o[q] * range;
+            m = (uint64_t)r[q] * range;
             if ((uint32_t)m >= thresh) return (uint32_t)(m >> 32);
         }
-        ++attempt;
     }
 }
 
@@ -91,16 +98,17 @@ static PhiloxPlan plan_philox(int32_t M)
     const double mean = (double)M / (double)(1 << lb);
     int cap = (int)(mean + 8.0 * sqrt(mean) + 16.0);
     cap |= 1;                                               // odd stride: no systematic bank conflicts
-    const size_t budget = 144 * 1024;
+    // the shuffle buffers reuse the space of the per-warp histograms, so that
+    // three CTAs fit one SM (occupancy matters more than shuffle threads)
+    const size_t hist = (size_t)PH_WARPS * ((size_t)1 << lb) * 4;
+    size_t budget = hist > (size_t)32 * 1024 ? hist : (size_t)32 * 1024;
     int t = (int)(budget / ((size_t)cap * 4));
     if (t > PH_THREADS) t = PH_THREADS;
     if (t < 1) t = 1;
     p.cap = cap;
     p.fy_threads = t;
-    const size_t hist = (size_t)(PH_WARPS + 1) * ((size_t)1 << lb) * 4 + 64;
-    const size_t fy = (size_t)t * cap * 4 + ((size_t)(1 << lb) + 1) * 4;
-    p.smem_bytes = hist > fy ? hist : fy;
-    p.smem_bytes += ((size_t)(1 << lb) + 1) * 4;            // bucket starts survive both phases
+    const size_t fy = (size_t)t * cap * 4;
+    p.smem_bytes = (hist > fy ? hist : fy) + ((size_t)(1 << lb) + 1) * 4 + 64;
     return p;
 }
 
@@ -117,8 +125,9 @@ __global__ void __launch_bounds__(PH_THREADS) perm_philox_kernel(int32_t M, int3
     __shared__ uint32_t scan_tot[PH_WARPS];
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    // contiguous element range of this warp (multiple of 32)
-    const int per_warp = (((M + PH_WARPS - 1) / PH_WARPS) + 31) & ~31;
+    // contiguous element range of this warp (multiple of 128: one Philox call
+    // per lane covers four consecutive bonds)
+    const int per_warp = (((M + PH_WARPS - 1) / PH_WARPS) + 127) & ~127;
     const int w_lo = min(M, warp * per_warp), w_hi = min(M, w_lo + per_warp);
 
     for (int run = blockIdx.x; run < R; run += gridDim.x) {
@@ -128,8 +137,13 @@ __global__ void __launch_bounds__(PH_THREADS) perm_philox_kernel(int32_t M, int3
         // ---- A: per-warp histograms of the bucket draws ----------------------
         for (int i = t; i < PH_WARPS * B; i += PH_THREADS) hist[i] = 0;
         __syncthreads();
-        for (int i = w_lo + lane; i < w_hi; i += 32)
-            atomicAdd(&hist[warp * B + philox_bucket(seed, (uint32_t)i, bmask)], 1u);
+        for (int i0 = w_lo + 4 * lane; i0 < w_hi; i0 += 128) {
+            uint32_t o[4];
+            philox_buckets4(seed, (uint32_t)i0 >> 2, o);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (i0 + q < w_hi) atomicAdd(&hist[warp * B + (o[q] & bmask)], 1u);
+        }
         __syncthreads();
 
         // ---- A': bucket starts (exclusive scan) and per-warp bases -----------
@@ -164,18 +178,31 @@ __global__ void __launch_bounds__(PH_THREADS) perm_philox_kernel(int32_t M, int3
         __syncthreads();
 
         // ---- B: stable scatter (order inside a bucket = ascending bond index) --
-        for (int i0 = w_lo; i0 < w_hi; i0 += 32) {
-            const int i = i0 + lane;
-            const bool valid = i < w_hi;
-            const uint32_t b = valid ? philox_bucket(seed, (uint32_t)i, bmask) : 0xffffffffu;
-            const uint32_t peers = __match_any_sync(0xffffffffu, b);
-            const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-            uint32_t pos = 0;
-            if (valid) pos = hist[warp * B + b] + rank;
-            __syncwarp();
-            if (valid && rank == 0) hist[warp * B + b] += __popc(peers);
-            __syncwarp();
-            if (valid) out[pos] = i;
+        for (int blk = w_lo; blk < w_hi; blk += 128) {
+            // lane l draws for bonds blk + 4l .. blk + 4l + 3, then the words are
+            // handed round so that in step j lane l ranks bond blk + 32 j + l
+            uint32_t o[4];
+            philox_buckets4(seed, (uint32_t)(blk + 4 * lane) >> 2, o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int src = 8 * j + (lane >> 2);
+                const uint32_t w0 = __shfl_sync(0xffffffffu, o[0], src);
+                const uint32_t w1 = __shfl_sync(0xffffffffu, o[1], src);
+                const uint32_t w2 = __shfl_sync(0xffffffffu, o[2], src);
+                const uint32_t w3 = __shfl_sync(0xffffffffu, o[3], src);
+                const uint32_t w = (lane & 2) ? ((lane & 1) ? w3 : w2) : ((lane & 1) ? w1 : w0);
+                const int i = blk + 32 * j + lane;
+                const bool valid = i < w_hi;
+                const uint32_t b = valid ? (w & bmask) : 0xffffffffu;
+                const uint32_t peers = __match_any_sync(0xffffffffu, b);
+                const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+                uint32_t pos = 0;
+                if (valid) pos = hist[warp * B + b] + rank;
+                __syncwarp();
+                if (valid && rank == 0) hist[warp * B + b] += __popc(peers);
+                __syncwarp();
+                if (valid) out[pos] = i;
+            }
         }
         __syncthreads();
 
@@ -188,15 +215,17 @@ __global__ void __launch_bounds__(PH_THREADS) perm_philox_kernel(int32_t M, int3
                     if ((int)sz <= cap) {
                         uint32_t *buf = fybuf + (size_t)t * cap;
                         for (uint32_t k = 0; k < sz; ++k) buf[k] = (uint32_t)out[s0 + k];
+                        uint32_t o[4], grp = 0xffffffffu;
                         for (uint32_t k = sz - 1; k >= 1; --k) {
-                            const uint32_t j = philox_bounded(seed, k, (uint32_t)b, k);
+                            const uint32_t j = philox_bounded(seed, (uint32_t)b, k, o, grp);
                             const uint32_t a = buf[k], c = buf[j];
                             buf[k] = c; buf[j] = a;
                         }
                         for (uint32_t k = 0; k < sz; ++k) out[s0 + k] = (int32_t)buf[k];
                     } else {                      // over-full bucket: same shuffle in place
+                        uint32_t o[4], grp = 0xffffffffu;
                         for (uint32_t k = sz - 1; k >= 1; --k) {
-                            const uint32_t j = philox_bounded(seed, k, (uint32_t)b, k);
+                            const uint32_t j = philox_bounded(seed, (uint32_t)b, k, o, grp);
                             const int32_t a = out[s0 + k], c = out[s0 + j];
                             out[s0 + k] = c; out[s0 + j] = a;
                         }

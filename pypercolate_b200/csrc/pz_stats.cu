@@ -183,7 +183,11 @@ __device__ __forceinline__ void halve_step(uint64_t (&v)[32], int lane) {
 }
 
 // checkpoints: run state after every `every`-th row, by a block-wide scan
-// (one CTA per run) -- lets accumulate / canon_runs start anywhere in a run
+// (one CTA per run, CK_ITEMS consecutive records per thread and chunk) -- lets
+// accumulate / canon_runs start anywhere in a run.  `every` must be a multiple
+// of CK_ITEMS.
+static constexpr int CK_ITEMS = 8;
+
 template <class RecT>
 __global__ void __launch_bounds__(ROWS_THREADS) checkpoint_kernel(StatsArgs a, RunState *ckpt,
                                                                    int every, int n_ckpt)
@@ -194,12 +198,22 @@ __global__ void __launch_bounds__(ROWS_THREADS) checkpoint_kernel(StatsArgs a, R
     const int run = blockIdx.x;
     const RecT *recs = reinterpret_cast<const RecT *>(a.recs) + (size_t)run * a.M;
     const int rows_total = a.M + 1;
+    constexpr int CHUNK = ROWS_THREADS * CK_ITEMS;
     if (t == 0) carry = Delta{0u, 1u, (uint64_t)a.N, (uint64_t)a.N, (uint64_t)a.N};
     __syncthreads();
-    for (int n0 = 0; n0 < rows_total; n0 += ROWS_THREADS) {
-        const int n = n0 + t;
-        Delta d{0, 0, 0, 0, 0};
-        if (n < rows_total && n >= 1) d = delta_of<RecT>(__ldg(&recs[n - 1]));
+    for (int n0 = 0; n0 < rows_total; n0 += CHUNK) {
+        const int first = n0 + t * CK_ITEMS;          // this thread's rows: first .. first+7
+        RecT r[CK_ITEMS];
+#pragma unroll
+        for (int i = 0; i < CK_ITEMS; ++i) {
+            const int n = first + i;
+            r[i] = (n >= 1 && n < rows_total) ? __ldg(&recs[n - 1]) : (RecT)0;
+        }
+        const Delta d0 = delta_of<RecT>(r[0]);        // first row of the thread
+        Delta d = d0;
+#pragma unroll
+        for (int i = 1; i < CK_ITEMS; ++i) d = delta_combine(d, delta_of<RecT>(r[i]));
+        const Delta mine = d;
 #pragma unroll
         for (int k = 1; k < 32; k <<= 1) {
             Delta o = delta_shfl_up(d, k);
@@ -209,13 +223,18 @@ __global__ void __launch_bounds__(ROWS_THREADS) checkpoint_kernel(StatsArgs a, R
         __syncthreads();
         Delta pre = carry;
         for (int w = 0; w < warp; ++w) pre = delta_combine(pre, warp_tot[w]);
-        d = delta_combine(pre, d);
+        // exclusive prefix of this thread = pre + (inclusive - mine): recombine from lane-1
+        Delta excl = delta_shfl_up(d, 1);
+        if (lane == 0) excl = Delta{0, 0, 0, 0, 0};
+        pre = delta_combine(pre, excl);
+        const Delta incl = delta_combine(pre, mine);
         __syncthreads();
-        if (t == ROWS_THREADS - 1) carry = d;
-        if (n < rows_total && (n % every) == 0) {
+        if (t == ROWS_THREADS - 1) carry = incl;
+        if (first < rows_total && (first % every) == 0) {
+            const Delta s0 = delta_combine(pre, d0);  // state after row `first`
             RunState st;
-            st.c = d.c; st.mx = d.mx; st.s2 = d.s2; st.s3 = d.s3; st.s4 = d.s4;
-            ckpt[(size_t)run * n_ckpt + n / every] = st;
+            st.c = s0.c; st.mx = s0.mx; st.s2 = s0.s2; st.s3 = s0.s3; st.s4 = s0.s4;
+            ckpt[(size_t)run * n_ckpt + first / every] = st;
         }
         __syncthreads();
     }

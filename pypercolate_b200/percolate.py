@@ -322,20 +322,24 @@ def _microcanonical_average_moments(moments, alpha):
 
 def _interval(mean, var, runs, alpha):
     """Student-t interval per n from device means / exact variances
-    (percolate/percolate.py:613-635, 681-705 vectorised over n)."""
+    (percolate/percolate.py:613-635, 681-705 vectorised over n).
+
+    ``scipy.stats.t.interval(1 - alpha, df, loc, scale)`` evaluates
+    ``t.ppf([alpha/2, 1 - alpha/2], df) * scale + loc``; the two quantiles
+    depend on ``(alpha, runs)`` only, so they are taken once and the affine
+    map is applied to all n -- the same floating-point operations the
+    reference performs for every n separately.
+    """
     std = np.sqrt(var)
     ci = np.empty(mean.shape + (2,))
     zero = (std == 0)
+    with np.errstate(invalid='ignore'):
+        q_lo, q_hi = scipy.stats.t.interval(1 - alpha, df=runs - 1)
+        scale = std / np.sqrt(runs)
+        ci[..., 0] = q_lo * scale + mean
+        ci[..., 1] = q_hi * scale + mean
     ci[zero, 0] = mean[zero]
     ci[zero, 1] = mean[zero]
-    nz = ~zero
-    if nz.any():
-        with np.errstate(invalid='ignore'):
-            lo, hi = scipy.stats.t.interval(
-                1 - alpha, df=runs - 1, loc=mean[nz],
-                scale=std[nz] / np.sqrt(runs))
-        ci[nz, 0] = lo
-        ci[nz, 1] = hi
     return ci
 
 
