@@ -178,10 +178,10 @@ cudaError_t launch_canon_rows(int32_t M, int spanning, const uint8_t *rows, cons
 // loads are warp-uniform.  Records go through the same padded tile as in
 // accumulate_kernel.
 // ---------------------------------------------------------------------------
-static constexpr int PC = 4;
+static constexpr int PC = 8;
 
 template <class RecT>
-__global__ void __launch_bounds__(128, 4) canon_runs_kernel(StatsArgs a, int32_t P, int32_t nchunks,
+__global__ void __launch_bounds__(128, 3) canon_runs_kernel(StatsArgs a, int32_t P, int32_t nchunks,
                                                           const double *pmf, const int32_t *band_lo,
                                                           const int32_t *band_hi, const int32_t *porder,
                                                           const RunState *ckpt, int ckpt_every,

@@ -13,8 +13,9 @@
 //
 //  * perm_philox: counter-based Philox4x32-10.  A uniform permutation is built
 //    in two exact steps (Rao-Sandelius): every bond draws one of B buckets
-//    uniformly and is placed by a STABLE counting sort (so the result does not
-//    depend on thread timing), then every bucket is shuffled by Fisher-Yates in
+//    uniformly and is placed by a counting sort whose buckets are kept in
+//    ascending bond order (so the result does not depend on thread timing),
+//    then every bucket is shuffled by Fisher-Yates in
 //    shared memory with unbiased (Lemire) bounded draws.  One CTA per run.
 //    Counters: bucket draws (i >> 2, 0, 0, 0) word i & 3; Fisher-Yates draw of
 //    step k of bucket b: word k & 3 of (k >> 2, b, 0, 1), on the (rare) Lemire
@@ -69,6 +70,7 @@ __device__ __forceinline__ uint32_t philox_bounded(uint32_t seed, uint32_t bucke
     }
     const uint32_t w = (k & 2u) ? ((k & 1u) ? o[3] : o[2]) : ((k & 1u) ? o[1] : o[0]);
     uint64_t m = (uint64_t)w * range;
+    if ((uint32_t)m >= range) return (uint32_t)(m >> 32);      // cannot be below the threshold
     const uint32_t thresh = (0u - range) % range;
     if ((uint32_t)m >= thresh) return (uint32_t)(m >> 32);
     for (uint32_t attempt = 1;; ++attempt) {
@@ -177,31 +179,17 @@ __global__ void __launch_bounds__(PH_THREADS) perm_philox_kernel(int32_t M, int3
         }
         __syncthreads();
 
-        // ---- B: stable scatter (order inside a bucket = ascending bond index) --
+        // ---- B: scatter.  Positions come from the per-warp bucket bases; two bonds
+        // of one warp instruction that share a bucket may land in either order, which
+        // phase C repairs by sorting the (almost sorted) bucket -- the order inside a
+        // bucket is ascending bond index whatever the timing.
         for (int blk = w_lo; blk < w_hi; blk += 128) {
-            // lane l draws for bonds blk + 4l .. blk + 4l + 3, then the words are
-            // handed round so that in step j lane l ranks bond blk + 32 j + l
             uint32_t o[4];
             philox_buckets4(seed, (uint32_t)(blk + 4 * lane) >> 2, o);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int src = 8 * j + (lane >> 2);
-                const uint32_t w0 = __shfl_sync(0xffffffffu, o[0], src);
-                const uint32_t w1 = __shfl_sync(0xffffffffu, o[1], src);
-                const uint32_t w2 = __shfl_sync(0xffffffffu, o[2], src);
-                const uint32_t w3 = __shfl_sync(0xffffffffu, o[3], src);
-                const uint32_t w = (lane & 2) ? ((lane & 1) ? w3 : w2) : ((lane & 1) ? w1 : w0);
-                const int i = blk + 32 * j + lane;
-                const bool valid = i < w_hi;
-                const uint32_t b = valid ? (w & bmask) : 0xffffffffu;
-                const uint32_t peers = __match_any_sync(0xffffffffu, b);
-                const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-                uint32_t pos = 0;
-                if (valid) pos = hist[warp * B + b] + rank;
-                __syncwarp();
-                if (valid && rank == 0) hist[warp * B + b] += __popc(peers);
-                __syncwarp();
-                if (valid) out[pos] = i;
+            for (int q = 0; q < 4; ++q) {
+                const int i = blk + 4 * lane + q;
+                if (i < w_hi) out[atomicAdd(&hist[warp * B + (o[q] & bmask)], 1u)] = i;
             }
         }
         __syncthreads();
@@ -215,6 +203,12 @@ __global__ void __launch_bounds__(PH_THREADS) perm_philox_kernel(int32_t M, int3
                     if ((int)sz <= cap) {
                         uint32_t *buf = fybuf + (size_t)t * cap;
                         for (uint32_t k = 0; k < sz; ++k) buf[k] = (uint32_t)out[s0 + k];
+                        for (uint32_t k = 1; k < sz; ++k) {       // restore ascending bond order
+                            const uint32_t v = buf[k];
+                            uint32_t j = k;
+                            while (j > 0 && buf[j - 1] > v) { buf[j] = buf[j - 1]; --j; }
+                            buf[j] = v;
+                        }
                         uint32_t o[4], grp = 0xffffffffu;
                         for (uint32_t k = sz - 1; k >= 1; --k) {
                             const uint32_t j = philox_bounded(seed, (uint32_t)b, k, o, grp);
@@ -222,7 +216,13 @@ __global__ void __launch_bounds__(PH_THREADS) perm_philox_kernel(int32_t M, int3
                             buf[k] = c; buf[j] = a;
                         }
                         for (uint32_t k = 0; k < sz; ++k) out[s0 + k] = (int32_t)buf[k];
-                    } else {                      // over-full bucket: same shuffle in place
+                    } else {                      // over-full bucket: same sort + shuffle in place
+                        for (uint32_t k = 1; k < sz; ++k) {
+                            const int32_t v = out[s0 + k];
+                            uint32_t j = k;
+                            while (j > 0 && out[s0 + j - 1] > v) { out[s0 + j] = out[s0 + j - 1]; --j; }
+                            out[s0 + j] = v;
+                        }
                         uint32_t o[4], grp = 0xffffffffu;
                         for (uint32_t k = sz - 1; k >= 1; --k) {
                             const uint32_t j = philox_bounded(seed, (uint32_t)b, k, o, grp);
