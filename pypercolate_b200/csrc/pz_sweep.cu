@@ -18,7 +18,8 @@
 //      one) is replayed in bond order, the whole warp walking together.
 //
 // The parent/size array of the run lives in shared memory whenever it fits
-// (uint16 entries; N <= 65536 covers the L = 256 square lattice in 136 KB),
+// (uint16 entries + one flag byte per node; N <= 65536 covers the L = 256 square
+// lattice in 192 KB),
 // otherwise in a per-warp slab of global memory that stays L2-resident.
 // Output per bond is one merge record (see pz_common.cuh); per run one word,
 // the first n at which the two spanning sides are joined (hpc.py:269-274).
@@ -118,105 +119,79 @@ struct StoreS16B {
     using Rec = uint32_t;
     using Edge = uint32_t;
     uint16_t *val;        // size-1 (root) or parent
-    uint32_t *rootbits;   // bit x: node x is a root
-    uint32_t *sides2;
+    uint8_t *flag;        // bit 0: root; bits 1-2: spanning sides touched by the cluster (roots)
     int32_t N;
     const uint32_t *sides_init;
 
-    static size_t slice_bytes(int32_t N) {
-        return align16h((size_t)N * 2) + align16h((size_t)((N + 31) / 32) * 4) +
-               align16h((size_t)((N + 15) / 16) * 4);
-    }
+    // token of a root: flag << 16 | size-1
+    static size_t slice_bytes(int32_t N) { return align16h((size_t)N * 2) + align16h((size_t)N); }
     __device__ void bind(unsigned char *slice, const SweepArgs &a, int) {
         N = a.N;
         val = reinterpret_cast<uint16_t *>(slice);
-        uint32_t off = align16((uint32_t)N * 2);
-        rootbits = reinterpret_cast<uint32_t *>(slice + off);
-        off += align16((uint32_t)((N + 31) / 32) * 4);
-        sides2 = reinterpret_cast<uint32_t *>(slice + off);
+        flag = slice + align16((uint32_t)N * 2);
         sides_init = a.sides2;
     }
     __device__ void init(int tid, int nthr) {
         uint4 *v128 = reinterpret_cast<uint4 *>(val);
         const int n128 = (N * 2 + 15) / 16;
         for (int i = tid; i < n128; i += nthr) v128[i] = make_uint4(0, 0, 0, 0);
-        for (int i = tid; i < (N + 31) / 32; i += nthr) rootbits[i] = 0xffffffffu;
-        if (sides_init)
-            for (int i = tid; i < (N + 15) / 16; i += nthr) sides2[i] = sides_init[i];
+        uint32_t *f32 = reinterpret_cast<uint32_t *>(flag);
+        for (int i = tid; i < (N + 3) / 4; i += nthr) {      // four nodes per word
+            uint32_t w = 0x01010101u;
+            if (sides_init) {
+                const uint32_t s = sides_init[i >> 2] >> ((i & 3) * 8);      // 4 x 2 bits
+                w |= ((s & 3u) << 1) | (((s >> 2) & 3u) << 9) | (((s >> 4) & 3u) << 17) |
+                     (((s >> 6) & 3u) << 25);
+            }
+            f32[i] = w;
+        }
     }
-    __device__ __forceinline__ bool is_root(uint32_t x) const {
-        return (rootbits[x >> 5] >> (x & 31u)) & 1u;
-    }
-    // The root bit is always read BEFORE the value (compiler barrier; shared
-    // memory accesses of one warp are performed in issue order) and unite()
-    // writes the parent pointer BEFORE clearing the bit, so a concurrent
-    // reader that sees "not a root" always reads a parent pointer, never a size.
     __device__ __forceinline__ uint32_t find(uint32_t x, uint32_t &tok) const {
-        bool rx = is_root(x);
-        asm volatile("" ::: "memory");
-        uint32_t vx = val[x];
-        while (!rx) {
+        uint32_t fx = flag[x], vx = val[x];
+        while (!(fx & 1u)) {
             const uint32_t p = vx;
-            const bool rp = is_root(p);
-            asm volatile("" ::: "memory");
-            const uint32_t vp = val[p];
-            if (rp) { x = p; vx = vp; break; }
-            val[x] = (uint16_t)vp;
+            const uint32_t fp = flag[p], vp = val[p];
+            if (fp & 1u) { x = p; fx = fp; vx = vp; break; }
+            val[x] = (uint16_t)vp;              // halve: parent[x] = grandparent
             x = vp;
-            rx = is_root(x);
-            asm volatile("" ::: "memory");
+            fx = flag[x];
             vx = val[x];
         }
-        tok = vx;
+        tok = (fx << 16) | vx;
         return x;
     }
     __device__ __forceinline__ void find2(uint32_t &x, uint32_t &y, uint32_t &tx, uint32_t &ty) const {
-        bool rx = is_root(x), ry = is_root(y);
-        asm volatile("" ::: "memory");
-        uint32_t vx = val[x], vy = val[y];
-        while (!(rx && ry)) {
-            if (!rx) x = vx;
-            if (!ry) y = vy;
-            rx = is_root(x);
-            ry = is_root(y);
-            asm volatile("" ::: "memory");
-            vx = val[x];
-            vy = val[y];
+        uint32_t fx = flag[x], fy = flag[y], vx = val[x], vy = val[y];
+        while (!(fx & fy & 1u)) {
+            if (!(fx & 1u)) x = vx;
+            if (!(fy & 1u)) y = vy;
+            fx = flag[x]; fy = flag[y];
+            vx = val[x]; vy = val[y];
         }
-        tx = vx; ty = vy;
+        tx = (fx << 16) | vx;
+        ty = (fy << 16) | vy;
     }
-    static __device__ __forceinline__ uint32_t size_m1(uint32_t tok) { return tok; }
-    __device__ __forceinline__ uint32_t side_of(uint32_t r) const {
-        return (sides2[r >> 4] >> ((r & 15u) * 2)) & 3u;
-    }
-    __device__ __forceinline__ uint32_t sides_of_root(uint32_t r, uint32_t) const { return side_of(r); }
+    static __device__ __forceinline__ uint32_t size_m1(uint32_t tok) { return tok & 0xffffu; }
+    __device__ __forceinline__ uint32_t sides_of_root(uint32_t, uint32_t tok) const { return (tok >> 17) & 3u; }
     __device__ __forceinline__ void make_child(uint32_t x, uint32_t parent) {
         val[x] = (uint16_t)parent;
-        asm volatile("" ::: "memory");
-        atomicAnd(&rootbits[x >> 5], ~(1u << (x & 31u)));
+        flag[x] = 0;
     }
     __device__ __forceinline__ void set_root(uint32_t r, uint32_t sz_m1, uint32_t add_sides) {
+        // only the designated thread of a star round calls this
         val[r] = (uint16_t)sz_m1;
-        if (add_sides) atomicOr(&sides2[r >> 4], add_sides << ((r & 15u) * 2));
+        if (add_sides) flag[r] = (uint8_t)(flag[r] | (add_sides << 1));
     }
+    // the winner owns both roots: plain stores, no atomics
     __device__ __forceinline__ uint32_t unite(uint32_t ra, uint32_t ta, uint32_t rb, uint32_t tb,
-                                              bool track) {
-        const uint32_t sa = ta, sb = tb;
+                                              bool) {
+        const uint32_t sa = size_m1(ta), sb = size_m1(tb);
         const uint32_t big = sa >= sb ? ra : rb, small = sa >= sb ? rb : ra;
+        const uint32_t m = ((ta | tb) >> 17) & 3u;
         val[small] = (uint16_t)big;
+        flag[small] = 0;
         val[big] = (uint16_t)(sa + sb + 1);
-#if PZ_STRICT_FENCE
-        __threadfence_block();
-#else
-        asm volatile("" ::: "memory");     // shared-memory stores of a warp are performed in order
-#endif
-        atomicAnd(&rootbits[small >> 5], ~(1u << (small & 31u)));
-        uint32_t m = 0;
-        if (track) {
-            const uint32_t mb = side_of(big);
-            m = mb | side_of(small);
-            if (m != mb) atomicOr(&sides2[big >> 4], m << ((big & 15u) * 2));
-        }
+        if (m != (((sa >= sb ? ta : tb) >> 17) & 3u)) flag[big] = (uint8_t)(1u | (m << 1));
         return m;
     }
 };
