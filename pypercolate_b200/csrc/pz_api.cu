@@ -97,11 +97,13 @@ struct pz_ctx {
     // canonical
     int32_t num_p = 0;
     int32_t pmf_M = -1;                   // number of bonds the weights were built for
+    int32_t sf_M = -1;                    // ... and the survival functions
     std::vector<double> ps;
     std::vector<int32_t> porder;          // sorted position -> caller's index
     DevBuf<double> ps_dev;
     DevBuf<double> pmf;                   // [num_p][M+1], rows in ascending-p order
-    DevBuf<int32_t> band_lo, band_hi, porder_dev;
+    DevBuf<int32_t> band_lo, band_hi, tband_lo, tband_hi, porder_dev, canon_flags;
+    DevBuf<double> sf;                    // survival functions [num_p][M+1]
     DevBuf<double> cols;                  // scratch of the contraction
     DevBuf<double> cols_out;
     const double *canon_last_ptr = nullptr;   // per-run values of the last chunk of the last fused call
@@ -159,16 +161,17 @@ cudaError_t launch_micro_finalize(int32_t N, int32_t M, int64_t runs, const unsi
                                   unsigned long long *span_cum, double *mean, double *var,
                                   cudaStream_t s);
 cudaError_t launch_binomial_pmf(int32_t M, int32_t P, const double *ps_dev, double *pmf,
-                                int32_t *band_lo, int32_t *band_hi, cudaStream_t s);
+                                int32_t *xlo, int32_t *xhi, int32_t *tlo, int32_t *thi, double *sf,
+                                cudaStream_t s);
 cudaError_t launch_convolve(int32_t M, int32_t P, const double *pmf, const int32_t *band_lo,
                             const int32_t *band_hi, int32_t num_cols, const double *cols,
                             double *out, cudaStream_t s);
 cudaError_t launch_canon_rows(int32_t M, int spanning, const uint8_t *rows, const double *f,
                               double *out, cudaStream_t s);
-cudaError_t launch_canon_runs(const StatsArgs &a, int32_t P, const double *pmf,
-                              const int32_t *band_lo, const int32_t *band_hi, const int32_t *porder,
-                              const RunState *ckpt, int ckpt_every, int n_ckpt, double *out,
-                              cudaStream_t s);
+cudaError_t launch_canon_runs(const StatsArgs &a, int32_t P, const double *pmf, const double *sf,
+                              const int32_t *xlo, const int32_t *xhi, const int32_t *tlo,
+                              const int32_t *thi, const int32_t *porder, const RunState *ckpt,
+                              int ckpt_every, int n_ckpt, double *out, int *flags, cudaStream_t s);
 cudaError_t launch_canon_reduce(int32_t R, int32_t cols, const double *runs, double *mean,
                                 double *m2, cudaStream_t s);
 cudaError_t launch_perm_philox(int32_t M, int32_t R, const uint32_t *seeds, int32_t *perms,
@@ -230,7 +233,8 @@ void pz_destroy(pz_ctx *c)
     }
     c->gscratch.release(); c->rows.release(); c->acc.release(); c->span_cum.release();
     c->fin.release(); c->ps_dev.release(); c->band_lo.release();
-    c->band_hi.release(); c->porder_dev.release(); c->cols.release(); c->cols_out.release();
+    c->band_hi.release(); c->tband_lo.release(); c->tband_hi.release(); c->canon_flags.release();
+    c->sf.release(); c->porder_dev.release(); c->cols.release(); c->cols_out.release();
     c->pmf.release();
     if (c->timer_a) { cudaEventDestroy(c->timer_a); cudaEventDestroy(c->timer_b); }
     cudaStreamDestroy(c->s_perm);
@@ -543,7 +547,7 @@ int pz_run_fused(pz_ctx *c, int32_t R, int perm_mode, const void *perm_src, int 
     int rc = check_run_args(c, R, perm_mode, perm_src);
     if (rc) return rc;
     if (!(flags & (PZ_FUSE_MICRO | PZ_FUSE_CANON))) return fail(PZ_ERR_ARG, "pz_run_fused: no flags");
-    if ((flags & PZ_FUSE_CANON) && (c->num_p == 0 || c->pmf_M != c->M))
+    if ((flags & PZ_FUSE_CANON) && (c->num_p == 0 || c->pmf_M != c->M || c->sf_M != c->M))
         return fail(PZ_ERR_STATE, "pz_run_fused: PZ_FUSE_CANON needs pz_set_ps(M = bonds of the graph) first");
     PZ_CUDA(cudaSetDevice(c->device));
     if (flags & PZ_FUSE_MICRO) { rc = ensure_acc(c); if (rc) return rc; }
@@ -593,16 +597,17 @@ int pz_run_fused(pz_ctx *c, int32_t R, int perm_mode, const void *perm_src, int 
             PZ_CUDA(sl.canon_red.ensure((size_t)2 * cols));
             {
                 PhaseTimer t(c, PZ_PHASE_CANON, ss);
-                PZ_CUDA(launch_canon_runs(ch.stats, P, c->pmf.p, c->band_lo.p, c->band_hi.p,
-                                          c->porder_dev.p, sl.ckpt.p, c->ckpt_every, n_ckpt,
-                                          sl.canon_runs.p, ss));
+                PZ_CUDA(launch_canon_runs(ch.stats, P, c->pmf.p, c->sf.p, c->band_lo.p, c->band_hi.p,
+                                          c->tband_lo.p, c->tband_hi.p, c->porder_dev.p, sl.ckpt.p,
+                                          c->ckpt_every, n_ckpt, sl.canon_runs.p, c->canon_flags.p,
+                                          ss));
             }
             {
                 PhaseTimer t(c, PZ_PHASE_REDUCE, ss);
                 PZ_CUDA(launch_canon_reduce(n, cols, sl.canon_runs.p, sl.canon_red.p,
                                             sl.canon_red.p + cols, ss));
             }
-            c->launches += 2;
+            c->launches += 3;
             if (sl.red_host_cap < (size_t)2 * cols) {
                 if (sl.red_host) cudaFreeHost(sl.red_host);
                 sl.red_host = nullptr; sl.red_host_cap = 0;
@@ -700,11 +705,18 @@ int pz_set_ps(pz_ctx *c, int32_t M, int32_t num_p, const double *ps, double *pmf
     PZ_CUDA(c->pmf.ensure((size_t)num_p * S));
     PZ_CUDA(c->band_lo.ensure(num_p));
     PZ_CUDA(c->band_hi.ensure(num_p));
+    PZ_CUDA(c->tband_lo.ensure(num_p));
+    PZ_CUDA(c->tband_hi.ensure(num_p));
+    PZ_CUDA(c->canon_flags.ensure(num_p));
+    const bool want_sf = c->N > 0 && M == c->M;      // only the fused path needs the table
+    if (want_sf) PZ_CUDA(c->sf.ensure((size_t)num_p * S));
     PZ_CUDA(c->porder_dev.ensure(num_p));
     PZ_CUDA(cudaMemcpyAsync(c->ps_dev.p, sorted.data(), (size_t)num_p * 8, cudaMemcpyHostToDevice, c->stream));
     PZ_CUDA(cudaMemcpyAsync(c->porder_dev.p, c->porder.data(), (size_t)num_p * 4, cudaMemcpyHostToDevice, c->stream));
-    PZ_CUDA(launch_binomial_pmf(M, num_p, c->ps_dev.p, c->pmf.p, c->band_lo.p, c->band_hi.p, c->stream));
-    c->launches += 2;
+    PZ_CUDA(launch_binomial_pmf(M, num_p, c->ps_dev.p, c->pmf.p, c->band_lo.p, c->band_hi.p,
+                                c->tband_lo.p, c->tband_hi.p, want_sf ? c->sf.p : nullptr, c->stream));
+    c->launches += want_sf ? 3 : 2;
+    c->sf_M = want_sf ? M : -1;
     if (pmf_out)
         for (int i = 0; i < num_p; ++i)
             PZ_CUDA(cudaMemcpyAsync(pmf_out + (size_t)c->porder[i] * S, c->pmf.p + (size_t)i * S, S * 8,

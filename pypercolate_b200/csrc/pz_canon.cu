@@ -5,7 +5,8 @@
 //   convolve          canonical_averages, percolate/percolate.py:1196-1221
 //   canon_rows        bond_canonical_statistics on host rows, percolate/hpc.py:488-515
 //   canon_runs        the same contraction for every run of a batch straight
-//                     from the merge records (nothing per-run materialised)
+//                     from the merge records (nothing per-run materialised);
+//                     tight band with a verified error bound + exact fallback
 //   canon_reduce      bond_initialize_canonical_averages + bond_reduce over the
 //                     runs of a batch, percolate/hpc.py:607-635, 664-702
 #include "pz_common.cuh"
@@ -59,43 +60,97 @@ __device__ __forceinline__ double block_sum(double v, double *sh)
     return t;
 }
 
-// normalise (ret / ret.sum()) and find the band [lo, hi] outside which the
-// weight is exactly zero (underflowed), so that banded sums drop no term
-static constexpr double PMF_EPS = 0.0;   // every non-zero weight is kept
-__global__ void __launch_bounds__(256) pmf_normalize_kernel(int32_t M, double *pmf, int32_t *band_lo,
-                                                             int32_t *band_hi)
+// normalise (ret / ret.sum()) and find two bands per p:
+//   exact band  [xlo, xhi]  outside which the weight is exactly zero (underflowed):
+//                           banded sums over it drop no term at all;
+//   tight band  [tlo, thi]  outside which the weight is below PMF_TIGHT: the dropped mass
+//                           is at most (M+1) * PMF_TIGHT, which bounds the error of a banded
+//                           sum absolutely (see canon_runs_kernel).
+static constexpr double PMF_TIGHT = 1e-40;
+__global__ void __launch_bounds__(256) pmf_normalize_kernel(int32_t M, double *pmf, int32_t *xlo,
+                                                             int32_t *xhi, int32_t *tlo, int32_t *thi)
 {
     __shared__ double sh[8];
-    __shared__ int s_lo, s_hi;
+    __shared__ int s_lo, s_hi, s_tlo, s_thi;
     double *ret = pmf + (size_t)blockIdx.x * ((size_t)M + 1);
     // chunked partial sums keep the association close to a pairwise sum
     double part = 0.0;
     for (int i = threadIdx.x; i <= M; i += blockDim.x) part += ret[i];
     const double s = block_sum(part, sh);
-    if (threadIdx.x == 0) { s_lo = M; s_hi = 0; }
+    if (threadIdx.x == 0) { s_lo = M; s_hi = 0; s_tlo = M; s_thi = 0; }
     __syncthreads();
-    int lo = M, hi = 0;
+    int lo = M, hi = 0, lo2 = M, hi2 = 0;
     for (int i = threadIdx.x; i <= M; i += blockDim.x) {
         const double v = __ddiv_rn(ret[i], s);
         ret[i] = v;
-        if (v > PMF_EPS) { lo = min(lo, i); hi = max(hi, i); }
+        if (v > 0.0) { lo = min(lo, i); hi = max(hi, i); }
+        if (v >= PMF_TIGHT) { lo2 = min(lo2, i); hi2 = max(hi2, i); }
     }
     atomicMin(&s_lo, lo);
     atomicMax(&s_hi, hi);
+    atomicMin(&s_tlo, lo2);
+    atomicMax(&s_thi, hi2);
     __syncthreads();
     if (threadIdx.x == 0) {
-        band_lo[blockIdx.x] = min(s_lo, s_hi);
-        band_hi[blockIdx.x] = max(s_lo, s_hi);
+        xlo[blockIdx.x] = min(s_lo, s_hi);
+        xhi[blockIdx.x] = max(s_lo, s_hi);
+        tlo[blockIdx.x] = min(s_tlo, s_thi);
+        thi[blockIdx.x] = max(s_tlo, s_thi);
+    }
+}
+
+// survival function sf[n] = sum_{m >= n} pmf[m] (one CTA per p, accumulated from
+// the top so that small tails keep their relative accuracy): the canonical
+// percolation probability of a run is sf[first spanning n] (hpc.py:495-499)
+static constexpr int SF_ITEMS = 8;
+__global__ void __launch_bounds__(256) pmf_sf_kernel(int32_t M, const double *pmf, double *sf)
+{
+    __shared__ double wtot[8];
+    __shared__ double carry;
+    const double *f = pmf + (size_t)blockIdx.x * ((size_t)M + 1);
+    double *out = sf + (size_t)blockIdx.x * ((size_t)M + 1);
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0) carry = 0.0;
+    __syncthreads();
+    for (long long top = M; top >= 0; top -= 256 * SF_ITEMS) {
+        const long long first = top - (long long)t * SF_ITEMS;       // this thread: first, first-1, ...
+        double v[SF_ITEMS], mine = 0.0;
+#pragma unroll
+        for (int i = 0; i < SF_ITEMS; ++i) {
+            const long long n = first - i;
+            v[i] = n >= 0 ? f[n] : 0.0;
+            mine += v[i];
+        }
+        double incl = mine;
+        for (int k = 1; k < 32; k <<= 1) {
+            const double o = __shfl_up_sync(0xffffffffu, incl, k);
+            if (lane >= k) incl += o;
+        }
+        if (lane == 31) wtot[warp] = incl;
+        __syncthreads();
+        double run = carry + (incl - mine);
+        for (int w = 0; w < warp; ++w) run += wtot[w];
+#pragma unroll
+        for (int i = 0; i < SF_ITEMS; ++i) {
+            const long long n = first - i;
+            run += v[i];
+            if (n >= 0) out[n] = run;
+        }
+        __syncthreads();
+        if (t == 255) carry = run;
+        __syncthreads();
     }
 }
 
 cudaError_t launch_binomial_pmf(int32_t M, int32_t P, const double *ps_dev, double *pmf,
-                                int32_t *band_lo, int32_t *band_hi, cudaStream_t s)
+                                int32_t *xlo, int32_t *xhi, int32_t *tlo, int32_t *thi, double *sf,
+                                cudaStream_t s)
 {
     if (P <= 0) return cudaSuccess;
     dim3 grid((P + 31) / 32, 2);
     binomial_pmf_kernel<<<grid, 32, 0, s>>>(M, P, ps_dev, pmf);
-    pmf_normalize_kernel<<<P, 256, 0, s>>>(M, pmf, band_lo, band_hi);
+    pmf_normalize_kernel<<<P, 256, 0, s>>>(M, pmf, xlo, xhi, tlo, thi);
+    if (sf) pmf_sf_kernel<<<P, 256, 0, s>>>(M, pmf, sf);
     return cudaGetLastError();
 }
 
@@ -172,20 +227,33 @@ cudaError_t launch_canon_rows(int32_t M, int spanning, const uint8_t *rows, cons
 // batch, straight from the merge records.
 //
 // One lane owns one run (a warp = 32 runs in lock step), one warp owns a chunk
-// of PC probabilities whose weights live in 7*PC register accumulators.  The
+// of PC probabilities whose weights live in 6*PC register accumulators.  The
 // warp starts at the last checkpoint (run state every `ckpt_every` rows, left
-// by accumulate_kernel) before the chunk's band and walks to its end; pmf
-// loads are warp-uniform.  Records go through the same padded tile as in
-// accumulate_kernel.
+// by checkpoint_kernel) before the chunk's band and walks to its end; records
+// and weights of a tile of rows are staged in shared memory.
+//
+// Column 0 (percolation probability) is not summed: the spanning flag is a
+// step function, so its contraction is the survival function at the first
+// spanning n -- one table look-up.
+//
+// Two passes.  Pass 0 sums over the TIGHT band (weights >= 1e-40); the dropped
+// terms are bounded by err = (M+1) * 1e-40 * 2^64 in absolute value, so every
+// result >= err * 1e11 is within 1e-11 relative of the full sum.  A chunk with
+// a smaller result raises a flag; pass 1 (same kernel, exact band = every
+// non-zero weight) recomputes only flagged chunks, so no term is ever dropped
+// from a result that could notice it.
 // ---------------------------------------------------------------------------
 static constexpr int PC = 8;
 
 template <class RecT>
 __global__ void __launch_bounds__(128, 3) canon_runs_kernel(StatsArgs a, int32_t P, int32_t nchunks,
-                                                          const double *pmf, const int32_t *band_lo,
-                                                          const int32_t *band_hi, const int32_t *porder,
-                                                          const RunState *ckpt, int ckpt_every,
-                                                          int n_ckpt, double *out)
+                                                             const double *pmf, const double *sf,
+                                                             const int32_t *xlo, const int32_t *xhi,
+                                                             const int32_t *tlo, const int32_t *thi,
+                                                             const int32_t *porder,
+                                                             const RunState *ckpt, int ckpt_every,
+                                                             int n_ckpt, double *out, int *flags,
+                                                             int pass)
 {
     constexpr int TILE = sizeof(RecT) == 4 ? 32 : 16;
     __shared__ RecT tile_all[4][32][TILE + 1];
@@ -197,6 +265,7 @@ __global__ void __launch_bounds__(128, 3) canon_runs_kernel(StatsArgs a, int32_t
     const int rg = (int)(wid / nchunks), ch = (int)(wid % nchunks);
     const int run0 = rg * 32;
     if (run0 >= a.R) return;
+    if (pass == 1 && flags[ch] == 0) return;          // nothing in this chunk needs the exact band
     const int run = run0 + lane;
     const bool live = run < a.R;
     const int M = a.M;
@@ -205,10 +274,15 @@ __global__ void __launch_bounds__(128, 3) canon_runs_kernel(StatsArgs a, int32_t
 
     // chunk band (sorted-p order)
     const int p0 = ch * PC, np = min(PC, P - p0);
+    const int32_t *blo = pass == 0 ? tlo : xlo, *bhi = pass == 0 ? thi : xhi;
     int lo = M, hi = 0;
+    bool narrowed = false;
 #pragma unroll
     for (int k = 0; k < PC; ++k)
-        if (k < np) { lo = min(lo, band_lo[p0 + k]); hi = max(hi, band_hi[p0 + k]); }
+        if (k < np) {
+            lo = min(lo, blo[p0 + k]); hi = max(hi, bhi[p0 + k]);
+            narrowed |= (tlo[p0 + k] != xlo[p0 + k]) || (thi[p0 + k] != xhi[p0 + k]);
+        }
     const int ck = lo / ckpt_every;                 // checkpoint row = ck * ckpt_every <= lo
     const int row_start = ck * ckpt_every;          // state is the one AFTER this row
     RunState st;
@@ -216,37 +290,36 @@ __global__ void __launch_bounds__(128, 3) canon_runs_kernel(StatsArgs a, int32_t
     if (live) st = ckpt[(size_t)run * n_ckpt + ck];
     const uint32_t nspan = (live && a.spanning) ? a.nspan[run] : NSPAN_NEVER;
 
-    double acc[PC][7];
+    double acc[PC][6];
 #pragma unroll
     for (int k = 0; k < PC; ++k)
 #pragma unroll
-        for (int q = 0; q < 7; ++q) acc[k][q] = 0.0;
+        for (int q = 0; q < 6; ++q) acc[k][q] = 0.0;
 
-    double x[7];
+    double x[6];
     bool dirty = true;
-    auto refresh = [&](int n) {
+    auto refresh = [&]() {
         if (dirty) {
             uint64_t m[5];
             st.moments((uint32_t)a.N, m);
-            x[0] = (uint32_t)n >= nspan ? 1.0 : 0.0;
-            x[1] = (double)st.mx;
+            x[0] = (double)st.mx;
 #pragma unroll
-            for (int k = 0; k < 5; ++k) x[2 + k] = (double)m[k];
+            for (int k = 0; k < 5; ++k) x[1 + k] = (double)m[k];
             dirty = false;
         }
     };
 
     // rows row_start .. hi; the state after row_start comes from the checkpoint,
-    // row n >= 1 applies record n-1.  Inside the union band every weight is
-    // used: outside its own band a weight is exactly 0.0 and contributes nothing.
+    // row n >= 1 applies record n-1.  Inside the union band of the chunk every
+    // weight is used (outside its own exact band a weight is exactly 0.0).
     int row = row_start;
     if (row >= lo) {
-        refresh(row);
+        refresh();
 #pragma unroll
         for (int k = 0; k < PC; ++k) {
             const double f = __ldg(&pmf[(size_t)min(p0 + k, P - 1) * S + row]);
 #pragma unroll
-            for (int q = 0; q < 7; ++q) acc[k][q] = fma(f, x[q], acc[k][q]);
+            for (int q = 0; q < 6; ++q) acc[k][q] = fma(f, x[q], acc[k][q]);
         }
     }
     while (row < hi) {
@@ -272,42 +345,55 @@ __global__ void __launch_bounds__(128, 3) canon_runs_kernel(StatsArgs a, int32_t
                 st.merge(RecCodec<RecT>::w_small(r), RecCodec<RecT>::w_large(r));
                 dirty = true;
             }
-            if ((uint32_t)nrow == nspan) dirty = true;
             if (nrow >= lo) {
-                refresh(nrow);
+                refresh();
 #pragma unroll
                 for (int k = 0; k < PC; ++k) {
                     const double f = ftile[k][j];
 #pragma unroll
-                    for (int q = 0; q < 7; ++q) acc[k][q] = fma(f, x[q], acc[k][q]);
+                    for (int q = 0; q < 6; ++q) acc[k][q] = fma(f, x[q], acc[k][q]);
                 }
             }
         }
         row += cnt;
     }
+    // error bound of the tight band: dropped mass * largest possible value
+    const double floor_ok = (double)(M + 1) * PMF_TIGHT * 18446744073709551616.0 * 1e11;
+    bool small = false;
     if (live) {
         for (int k = 0; k < np; ++k) {
             double *o = out + ((size_t)run * P + porder[p0 + k]) * 7;
-            for (int q = 0; q < 7; ++q) o[q] = acc[k][q];
+            o[0] = (nspan != NSPAN_NEVER && nspan <= (uint32_t)M) ? __ldg(&sf[(size_t)(p0 + k) * S + nspan]) : 0.0;
+            for (int q = 0; q < 6; ++q) {
+                o[1 + q] = acc[k][q];
+                small |= acc[k][q] < floor_ok;
+            }
         }
     }
+    if (pass == 0 && narrowed && __any_sync(0xffffffffu, small) && lane == 0) atomicOr(&flags[ch], 1);
 }
 
-cudaError_t launch_canon_runs(const StatsArgs &a, int32_t P, const double *pmf,
-                              const int32_t *band_lo, const int32_t *band_hi, const int32_t *porder,
-                              const RunState *ckpt, int ckpt_every, int n_ckpt, double *out,
-                              cudaStream_t s)
+cudaError_t launch_canon_runs(const StatsArgs &a, int32_t P, const double *pmf, const double *sf,
+                              const int32_t *xlo, const int32_t *xhi, const int32_t *tlo,
+                              const int32_t *thi, const int32_t *porder, const RunState *ckpt,
+                              int ckpt_every, int n_ckpt, double *out, int *flags, cudaStream_t s)
 {
     if (a.R <= 0 || P <= 0) return cudaSuccess;
     const int nchunks = (P + PC - 1) / PC;
     const long long warps = (long long)((a.R + 31) / 32) * nchunks;
     const int grid = (int)((warps + 3) / 4);
-    if (a.rec64)
-        canon_runs_kernel<uint64_t><<<grid, 128, 0, s>>>(a, P, nchunks, pmf, band_lo, band_hi, porder,
-                                                          ckpt, ckpt_every, n_ckpt, out);
-    else
-        canon_runs_kernel<uint32_t><<<grid, 128, 0, s>>>(a, P, nchunks, pmf, band_lo, band_hi, porder,
-                                                          ckpt, ckpt_every, n_ckpt, out);
+    cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(int) * nchunks, s);
+    if (e != cudaSuccess) return e;
+    for (int pass = 0; pass < 2; ++pass) {
+        if (a.rec64)
+            canon_runs_kernel<uint64_t><<<grid, 128, 0, s>>>(a, P, nchunks, pmf, sf, xlo, xhi, tlo, thi,
+                                                              porder, ckpt, ckpt_every, n_ckpt, out,
+                                                              flags, pass);
+        else
+            canon_runs_kernel<uint32_t><<<grid, 128, 0, s>>>(a, P, nchunks, pmf, sf, xlo, xhi, tlo, thi,
+                                                              porder, ckpt, ckpt_every, n_ckpt, out,
+                                                              flags, pass);
+    }
     return cudaGetLastError();
 }
 
