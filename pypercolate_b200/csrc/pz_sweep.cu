@@ -486,22 +486,30 @@ __global__ void __launch_bounds__(32 * CTA_WARPS, 1) sweep_cta_kernel(SweepArgs 
             bool pending = valid && ru != rv;
             Rec rec = 0;
             for (;;) {
+                // a warp without pending bonds only takes part in the barriers
+                const bool warp_has = __any_sync(0xffffffffu, pending);
                 const uint32_t key = (epoch << 10) | (uint32_t)tid;
-                const uint32_t hub = (uint32_t)sh->hub_key;
-                // star bond: one side is the hub; o = the other root
-                const bool star = pending && (ru == hub || rv == hub);
-                const uint32_t o = ru == hub ? rv : ru, to = ru == hub ? tv : tu;
-                const uint32_t th = ru == hub ? tu : tv;
-                uint32_t su = 0, sv = 0;
-                if (pending) {
-                    su = claim_slot(star ? o : ru, clog);
-                    sv = claim_slot(star ? o : rv, clog);
-                    atomicMin(&claim[su], key);
-                    if (!star) atomicMin(&claim[sv], key);
+                uint32_t hub = 0, o = 0, to = 0, th = 0, su = 0, sv = 0;
+                bool star = false;
+                if (warp_has) {
+                    hub = (uint32_t)sh->hub_key;
+                    // star bond: one side is the hub; o = the other root
+                    star = pending && (ru == hub || rv == hub);
+                    o = ru == hub ? rv : ru; to = ru == hub ? tv : tu;
+                    th = ru == hub ? tu : tv;
+                    if (pending) {
+                        su = claim_slot(star ? o : ru, clog);
+                        sv = claim_slot(star ? o : rv, clog);
+                        atomicMin(&claim[su], key);
+                        if (!star) atomicMin(&claim[sv], key);
+                    }
                 }
                 if (!__syncthreads_or(pending)) break;          // nothing (left) to merge
-                const bool own = pending && claim[su] == key && claim[sv] == key;
-                if (pending && !own) atomicMin(&sh->bmin, (uint32_t)tid);
+                bool own = false;
+                if (warp_has) {
+                    own = pending && claim[su] == key && claim[sv] == key;
+                    if (pending && !own) atomicMin(&sh->bmin, (uint32_t)tid);
+                }
                 const int nstar = __syncthreads_count(own && star);
                 bool won = false;
                 if (own && !star) {
@@ -517,26 +525,29 @@ __global__ void __launch_bounds__(32 * CTA_WARPS, 1) sweep_cta_kernel(SweepArgs 
                 if (nstar) {
                     // star bonds merge together iff no earlier bond of the batch is blocked
                     const bool sw = own && star && (uint32_t)tid < sh->bmin;
-                    const uint32_t so = sw ? st.sides_of_root(o, to) : 0u;
-                    unsigned long long v = sw ? ((unsigned long long)(Store::size_m1(to) + 1) |
-                                                 ((unsigned long long)(so & 1u) << 40) |
-                                                 ((unsigned long long)(so >> 1) << 50)) : 0ull;
-                    unsigned long long incl = v;
+                    unsigned long long v = 0ull, incl = 0ull;
+                    if (__any_sync(0xffffffffu, sw)) {
+                        const uint32_t so = sw ? st.sides_of_root(o, to) : 0u;
+                        v = sw ? ((unsigned long long)(Store::size_m1(to) + 1) |
+                                  ((unsigned long long)(so & 1u) << 40) |
+                                  ((unsigned long long)(so >> 1) << 50)) : 0ull;
+                        incl = v;
 #pragma unroll
-                    for (int k = 1; k < 32; k <<= 1) {
-                        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, k);
-                        if (lane >= k) incl += t;
+                        for (int k = 1; k < 32; k <<= 1) {
+                            const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, k);
+                            if (lane >= k) incl += t;
+                        }
                     }
                     if (lane == 31) sh->scan_tot[warp] = incl;
                     __syncthreads();
-                    unsigned long long pre = incl - v, total = 0;
-#pragma unroll
-                    for (int w = 0; w < CTA_WARPS; ++w) {
-                        const unsigned long long t = sh->scan_tot[w];
-                        if (w < warp) pre += t;
-                        total += t;
-                    }
                     if (sw) {
+                        unsigned long long pre = incl - v, total = 0;
+#pragma unroll
+                        for (int w = 0; w < CTA_WARPS; ++w) {
+                            const unsigned long long t = sh->scan_tot[w];
+                            if (w < warp) pre += t;
+                            total += t;
+                        }
                         const uint32_t hub_m1 = Store::size_m1(th);     // hub size - 1 at round start
                         const uint32_t pre_sz = (uint32_t)(pre & 0xffffffffffull);
                         rec = make_rec<Rec>(Store::size_m1(to), hub_m1 + pre_sz);
