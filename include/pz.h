@@ -39,7 +39,10 @@ enum pz_perm_mode {
     PZ_PERM_DEVICE = 1,    /* same layout, pointer is device memory                      */
     PZ_PERM_MT19937 = 2,   /* uint32 seeds[R]; numpy RandomState(seed).permutation(M)
                               reproduced on the device bit for bit                      */
-    PZ_PERM_PHILOX = 3     /* uint32 seeds[R]; Philox4x32-10 bucketed Fisher-Yates       */
+    PZ_PERM_PHILOX = 3,    /* uint32 seeds[R]; Philox4x32-10 bucketed Fisher-Yates       */
+    PZ_PERM_FEISTEL = 4    /* uint32 seeds[R]; Philox-keyed 20-round Feistel bijection of
+                              [0, M) with cycle walking: order[n] = pi_seed(n), no
+                              scratch and no shared memory (the throughput mode)        */
 };
 
 /* OR into a device-RNG perm_mode when the seeds already live in device memory */
@@ -91,7 +94,7 @@ int pz_run_rows(pz_ctx *ctx, int32_t R, int perm_mode, const void *perm_src,
 
 /*
  * Bond orders only: the device replacement of RandomState(seed).permutation(M)
- * (percolate/hpc.py:195,206).  perm_mode is PZ_PERM_MT19937 or PZ_PERM_PHILOX;
+ * (percolate/hpc.py:195,206).  perm_mode is PZ_PERM_MT19937, PZ_PERM_PHILOX or PZ_PERM_FEISTEL;
  * seeds host uint32[R]; out int32[R][M] (host, or device when is_device != 0).
  */
 int pz_make_perms(pz_ctx *ctx, int32_t R, int perm_mode, const uint32_t *seeds,
@@ -194,7 +197,7 @@ int pz_canon_last_runs(pz_ctx *ctx, double *out);
  * the counters).  ms_out / launches_out have PZ_PHASES entries.
  */
 #define PZ_PHASES 7
-#define PZ_PHASE_PERM 0     /* bond orders (Philox / MT19937)       */
+#define PZ_PHASE_PERM 0     /* bond orders (device RNG modes)        */
 #define PZ_PHASE_SWEEP 1    /* union-find sweep                      */
 #define PZ_PHASE_ACCUM 2    /* per-n exact sums over runs            */
 #define PZ_PHASE_CANON 3    /* per-run binomial contraction          */

@@ -15,9 +15,11 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpz_b200.so")
+LIB_PATH = os.environ.get("PZ_B200_LIB") or os.path.join(_HERE, "libpz_b200.so")   # env: A/B builds
 
-PERM_HOST, PERM_DEVICE, PERM_MT19937, PERM_PHILOX = 0, 1, 2, 3
+PERM_HOST, PERM_DEVICE, PERM_MT19937, PERM_PHILOX, PERM_FEISTEL = 0, 1, 2, 3, 4
+# rng keyword of the Python API -> perm_mode
+RNG_MODES = {'mt19937': PERM_MT19937, 'philox': PERM_PHILOX, 'feistel': PERM_FEISTEL}
 FUSE_MICRO, FUSE_CANON = 1, 2
 SEEDS_ON_DEVICE = 0x100
 ACC_WORDS = 25

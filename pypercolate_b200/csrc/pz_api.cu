@@ -178,6 +178,8 @@ cudaError_t launch_perm_philox(int32_t M, int32_t R, const uint32_t *seeds, int3
                                cudaStream_t s, int *launches);
 cudaError_t launch_perm_mt19937(int32_t M, int32_t R, const uint32_t *seeds, int32_t *perms,
                                 cudaStream_t s, int *launches);
+cudaError_t launch_perm_feistel(int32_t M, int32_t R, const uint32_t *seeds, int32_t *perms,
+                                cudaStream_t s, int *launches);
 }
 
 extern "C" {
@@ -352,6 +354,8 @@ static int sweep_chunk(pz_ctx *c, pz_ctx::Slot &sl, cudaStream_t sp, int32_t R, 
             PhaseTimer t(c, PZ_PHASE_PERM, sp);
             if (perm_mode == PZ_PERM_PHILOX)
                 PZ_CUDA(launch_perm_philox(M, R, seeds_dev, sl.perms.p, sp, &l));
+            else if (perm_mode == PZ_PERM_FEISTEL)
+                PZ_CUDA(launch_perm_feistel(M, R, seeds_dev, sl.perms.p, sp, &l));
             else
                 PZ_CUDA(launch_perm_mt19937(M, R, seeds_dev, sl.perms.p, sp, &l));
             c->launches += l;
@@ -399,7 +403,7 @@ static int check_run_args(pz_ctx *c, int32_t R, int perm_mode, const void *perm_
     if (c->N == 0) return fail(PZ_ERR_STATE, "no graph set (call pz_set_graph first)");
     if (R < 0) return fail(PZ_ERR_ARG, "R must be >= 0");
     const int base_mode = perm_mode & ~PZ_SEEDS_ON_DEVICE;
-    if (base_mode < PZ_PERM_HOST || base_mode > PZ_PERM_PHILOX)
+    if (base_mode < PZ_PERM_HOST || base_mode > PZ_PERM_FEISTEL)
         return fail(PZ_ERR_ARG, "unknown perm_mode");
     if ((perm_mode & PZ_SEEDS_ON_DEVICE) && base_mode < PZ_PERM_MT19937)
         return fail(PZ_ERR_ARG, "PZ_SEEDS_ON_DEVICE needs a device RNG mode");
@@ -485,7 +489,7 @@ int pz_make_perms(pz_ctx *c, int32_t R, int perm_mode, const uint32_t *seeds, in
 {
     if (!c) return fail(PZ_ERR_ARG, "null context");
     if (c->N == 0) return fail(PZ_ERR_STATE, "no graph set (call pz_set_graph first)");
-    if (perm_mode != PZ_PERM_MT19937 && perm_mode != PZ_PERM_PHILOX)
+    if (perm_mode != PZ_PERM_MT19937 && perm_mode != PZ_PERM_PHILOX && perm_mode != PZ_PERM_FEISTEL)
         return fail(PZ_ERR_ARG, "pz_make_perms: perm_mode must be a device RNG mode");
     if (R < 0 || (R > 0 && (!seeds || !out))) return fail(PZ_ERR_ARG, "pz_make_perms: bad arguments");
     if (R == 0 || c->M == 0) return PZ_OK;
@@ -504,6 +508,7 @@ int pz_make_perms(pz_ctx *c, int32_t R, int perm_mode, const uint32_t *seeds, in
         {
             PhaseTimer t(c, PZ_PHASE_PERM);
             if (perm_mode == PZ_PERM_PHILOX) PZ_CUDA(launch_perm_philox(c->M, n, sl.seeds.p, dst, c->stream, &l));
+            else if (perm_mode == PZ_PERM_FEISTEL) PZ_CUDA(launch_perm_feistel(c->M, n, sl.seeds.p, dst, c->stream, &l));
             else PZ_CUDA(launch_perm_mt19937(c->M, n, sl.seeds.p, dst, c->stream, &l));
         }
         c->launches += l;
@@ -565,7 +570,7 @@ int pz_run_fused(pz_ctx *c, int32_t R, int perm_mode, const void *perm_src, int 
     }
     const int n_ckpt = c->M / c->ckpt_every + 1;
     cudaStream_t sp = c->pipeline ? c->s_perm : c->stream;
-    cudaStream_t ss = c->pipeline ? c->s_stats : c->stream;
+    cudaStream_t ss = c->pipeline == 1 ? c->s_stats : c->stream;    // 2: only the bond orders overlap
     size_t ci = 0;
     for (size_t r0 = 0; r0 < (size_t)R; r0 += chunk, ++ci) {
         const int32_t n = (int32_t)std::min(chunk, (size_t)R - r0);

@@ -22,6 +22,21 @@
 //    rejection words 0.. of (k, b, attempt >= 1, 2).  Key: (seed, 0x50455243).
 //    Every Philox call therefore serves four bonds.
 //    oracle/pz_oracle.c restates this algorithm on the CPU for bit-exact tests.
+//
+//  * perm_feistel: the bond order as a keyed BIJECTION of [0, M): position n ->
+//    bond pi_seed(n), evaluated independently per position -- no scatter, no
+//    atomics, no shared memory, one coalesced write.  pi is an alternating
+//    unbalanced Feistel network over the 2^k >= M points (k = ceil(log2 M),
+//    halves of k/2 and k - k/2 bits that swap roles every round), 20 rounds,
+//    round function = both words of the 64-bit product (R ^ key_i) * 0xD2511F53
+//    xor-ed together (the Philox multiplier), round keys = Philox4x32-10 words of
+//    counter (i >> 2, 0, 0, 3) under key (seed, 'PERC'); points that land at or
+//    above M are walked on (cycle walking) until they fall below M, which keeps
+//    the map a bijection of [0, M).  A pseudo-random permutation family rather
+//    than an exact uniform shuffle; tests/test_oracle.py checks it against the
+//    uniform distribution over ALL permutations on small domains and by order
+//    statistics on large ones, tests/test_gpu_parity.py against the reference's
+//    confidence intervals.
 #include "pz_common.cuh"
 #include "pz_internal.h"
 
@@ -250,6 +265,70 @@ cudaError_t launch_perm_philox(int32_t M, int32_t R, const uint32_t *seeds, int3
     perm_philox_kernel<<<R, PH_THREADS, p.smem_bytes, s>>>(M, R, seeds, perms, p.log2_buckets, p.cap,
                                                            p.fy_threads);
     *launches = 1;
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// keyed bijection (Feistel network with cycle walking)
+// ---------------------------------------------------------------------------
+static constexpr int FEISTEL_ROUNDS = 20;
+static constexpr int FE_THREADS = 256;
+static constexpr int FE_ITEMS = 8;             // positions per thread
+
+__global__ void __launch_bounds__(FE_THREADS) perm_feistel_kernel(int32_t M, int32_t R,
+                                                                  const uint32_t *seeds, int32_t *perms,
+                                                                  int k_bits)
+{
+    __shared__ uint32_t keys[FEISTEL_ROUNDS];
+    const int run = blockIdx.y;
+    if (threadIdx.x < FEISTEL_ROUNDS / 4) {
+        uint32_t o[4];
+        philox4x32_10(seeds[run], PHILOX_KEY1, (uint32_t)threadIdx.x, 0u, 0u, 3u, o);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) keys[4 * threadIdx.x + q] = o[q];
+    }
+    __syncthreads();
+    uint32_t key[FEISTEL_ROUNDS];
+#pragma unroll
+    for (int i = 0; i < FEISTEL_ROUNDS; ++i) key[i] = keys[i];
+
+    const int a = k_bits >> 1, b = k_bits - a;
+    const uint32_t mb = (1u << b) - 1u;
+    const int sh = 32 - a;
+    int32_t *out = perms + (size_t)run * M;
+    const int base = blockIdx.x * (FE_THREADS * FE_ITEMS) + threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < FE_ITEMS; ++j) {
+        const int n = base + j * FE_THREADS;
+        if (n >= M) break;
+        uint32_t x = (uint32_t)n;
+        do {
+#pragma unroll
+            for (int i = 0; i < FEISTEL_ROUNDS; ++i) {
+                const uint32_t r = x & mb;
+                const uint64_t pr = (uint64_t)(r ^ key[i]) * 0xD2511F53u;
+                const uint32_t f = (uint32_t)(pr >> 32) ^ (uint32_t)pr;
+                x = (r << a) | ((x >> b) ^ (f >> sh));
+            }
+        } while (x >= (uint32_t)M);
+        out[n] = (int32_t)x;
+    }
+}
+
+cudaError_t launch_perm_feistel(int32_t M, int32_t R, const uint32_t *seeds, int32_t *perms,
+                                cudaStream_t s, int *launches)
+{
+    *launches = 0;
+    if (R <= 0 || M <= 0) return cudaSuccess;
+    int k = 2;
+    while (((long long)1 << k) < M) ++k;
+    const int per_block = FE_THREADS * FE_ITEMS;
+    for (int r0 = 0; r0 < R; r0 += 65535) {         // gridDim.y limit
+        const int rn = R - r0 < 65535 ? R - r0 : 65535;
+        dim3 grid((unsigned)((M + per_block - 1) / per_block), (unsigned)rn);
+        perm_feistel_kernel<<<grid, FE_THREADS, 0, s>>>(M, rn, seeds + r0, perms + (size_t)r0 * M, k);
+        *launches += 1;
+    }
     return cudaGetLastError();
 }
 

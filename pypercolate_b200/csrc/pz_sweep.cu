@@ -66,6 +66,10 @@ struct StoreS16 {
         if (sides_init)
             for (int i = tid; i < (N + 15) / 16; i += nthr) sides2[i] = sides_init[i];
     }
+    __device__ __forceinline__ void find_pair(uint32_t &x, uint32_t &y, uint32_t &tx, uint32_t &ty) const {
+        x = find(x, tx);
+        y = find(y, ty);
+    }
     __device__ __forceinline__ uint32_t find(uint32_t x, uint32_t &tok) const {
         uint32_t vx = val[x];
         while (!(vx & 0x8000u)) {
@@ -145,6 +149,10 @@ struct StoreS16B {
             }
             f32[i] = w;
         }
+    }
+    __device__ __forceinline__ void find_pair(uint32_t &x, uint32_t &y, uint32_t &tx, uint32_t &ty) const {
+        x = find(x, tx);
+        y = find(y, ty);
     }
     __device__ __forceinline__ uint32_t find(uint32_t x, uint32_t &tok) const {
         uint32_t fx = flag[x], vx = val[x];
@@ -226,6 +234,20 @@ struct StoreG32 {
         }
         tok = vx;
         return x;
+    }
+    // both endpoints of a bond at once: two independent chains in lock step (the
+    // store is L2 resident, so the two dependent-load chains overlap), path
+    // splitting: every node visited is re-pointed at its grandparent
+    __device__ __forceinline__ void find_pair(uint32_t &x, uint32_t &y, uint32_t &tx, uint32_t &ty) const {
+        uint32_t px = 0xffffffffu, py = 0xffffffffu;
+        uint32_t vx = val[x], vy = val[y];
+        while (!((vx & vy) >> 31)) {
+            if (!(vx >> 31)) { if (px != 0xffffffffu) val[px] = vx; px = x; x = vx; }
+            if (!(vy >> 31)) { if (py != 0xffffffffu) val[py] = vy; py = y; y = vy; }
+            vx = val[x];
+            vy = val[y];
+        }
+        tx = vx; ty = vy;
     }
     __device__ __forceinline__ void find2(uint32_t &x, uint32_t &y, uint32_t &tx, uint32_t &ty) const {
         uint32_t vx = val[x], vy = val[y];
@@ -419,7 +441,7 @@ __global__ void sweep_kernel(SweepArgs a, uint32_t slice_bytes)
 // the same run, and every dependent-latency chain (find, claim, merge) is paid
 // once per CTA_THREADS bonds instead of once per 32.
 // ---------------------------------------------------------------------------
-static constexpr int CTA_MAX_WARPS = 16;
+static constexpr int CTA_MAX_WARPS = 32;
 
 struct CtaShared {
     unsigned long long hub_key;               // (size << 32) | root of the largest cluster seen
@@ -478,10 +500,8 @@ __global__ void __launch_bounds__(32 * CTA_WARPS, 1) sweep_cta_kernel(SweepArgs 
 
             uint32_t ru = 0, rv = 0, tu = 0, tv = 0;
             if (valid) {
-                uint32_t u, v;
-                edge_uv(uv, u, v);
-                ru = st.find(u, tu);
-                rv = st.find(v, tv);
+                edge_uv(uv, ru, rv);
+                st.find_pair(ru, rv, tu, tv);
             }
             bool pending = valid && ru != rv;
             Rec rec = 0;
@@ -601,7 +621,7 @@ static SweepPlan plan_team(SweepPlan p, int32_t N, int32_t R, int sms, size_t sm
     // the 64-warp limit allow.  Claim table: exact (one slot per node) when it
     // fits next to the store, else as large as fits (hashed).
     const size_t sm_total = 228 * 1024;
-    const size_t fixed = store_bytes + 192;    // + CtaShared
+    const size_t fixed = store_bytes + 320;    // + CtaShared
     const int CTA_WARPS = cta_warps;
     int clog = ilog2_ceil((uint32_t)(N < 256 ? 256 : N));
     if (claim_cap < 8) claim_cap = 8;
@@ -653,12 +673,12 @@ SweepPlan plan_sweep(int32_t N, int32_t R, int sms, size_t smem_optin, int force
         int w = cta_warps, cap = claim_cap;
         if (w <= 0) {
             const size_t sb = align16h(store_bytes);
-            const int fit = (int)((228 * 1024) / (sb + ((size_t)4 << 12) + 1024 + 192));
+            const int fit = (int)((228 * 1024) / (sb + ((size_t)4 << 12) + 1024 + 320));
             w = fit >= 4 ? 4 : fit >= 2 ? 8 : 16;
             if (cap <= 0) cap = fit >= 2 ? 12 : 14;
         }
         if (cap <= 0) cap = 12;
-        w = w <= 2 ? 2 : w <= 4 ? 4 : w <= 8 ? 8 : 16;
+        w = w <= 2 ? 2 : w <= 4 ? 4 : w <= 8 ? 8 : w <= 16 ? 16 : 32;
         return plan_team(p, N, R, sms, smem_optin, align16h(store_bytes), cap, w);
     }
     p.slice_bytes = align16h(store_bytes + ((size_t)4 << clog));
@@ -712,6 +732,7 @@ static cudaError_t launch_team_t(const SweepPlan &p, const SweepArgs &a, cudaStr
     case 2: return launch_team_w<Store, 2>(p, a, s);
     case 4: return launch_team_w<Store, 4>(p, a, s);
     case 8: return launch_team_w<Store, 8>(p, a, s);
+    case 32: return launch_team_w<Store, 32>(p, a, s);
     default: return launch_team_w<Store, 16>(p, a, s);
     }
 }

@@ -91,9 +91,11 @@ def _run_rows(lowered, seeds, device=None, rng='mt19937'):
     """Rows of the runs seeded by ``seeds`` (shape (R, M+1))."""
     ctx = _native.context_for(lowered, _default_device() if device is None else device)
     seeds = list(seeds)
-    if rng == 'philox':
-        return ctx.run_rows(len(seeds), _native.PERM_PHILOX,
+    if rng in ('philox', 'feistel'):
+        return ctx.run_rows(len(seeds), _native.RNG_MODES[rng],
                             np.asarray(seeds, dtype=np.uint32))
+    if rng != 'mt19937':
+        raise ValueError("rng must be 'mt19937', 'philox' or 'feistel'")
     if all(_is_u32_seed(s) for s in seeds):
         # numpy's legacy stream reproduced on the device, bit for bit
         return ctx.run_rows(len(seeds), _native.PERM_MT19937,
@@ -126,7 +128,8 @@ def bond_sample_states(
     ``pypercolate_b200.lowering.LoweredGraph``.  Backend-only keyword
     arguments: ``device`` (CUDA device index), ``rng`` (``'mt19937'`` --
     numpy's ``RandomState(seed).permutation`` reproduced bit for bit, the
-    default -- or ``'philox'``).
+    default --, ``'philox'`` (Philox4x32-10 bucketed Fisher-Yates) or
+    ``'feistel'`` (Philox-keyed Feistel bijection, the throughput mode)).
 
     Yields
     ------
@@ -504,9 +507,9 @@ def bond_canonical_averages_batch(
     seeds = np.asarray(seeds, dtype=np.uint32)
     ctx.set_ps(np.asarray(ps, dtype=np.float64))
     ctx.reset_accumulators()
-    ctx.run_fused(seeds.size,
-                  _native.PERM_PHILOX if rng == 'philox' else _native.PERM_MT19937,
-                  seeds, _native.FUSE_CANON)
+    if rng not in _native.RNG_MODES:
+        raise ValueError("rng must be 'mt19937', 'philox' or 'feistel'")
+    ctx.run_fused(seeds.size, _native.RNG_MODES[rng], seeds, _native.FUSE_CANON)
     count, mean, m2 = ctx.canon_export()
     return _canonical_averages_from_partials(count, mean, m2, spanning_cluster)
 
@@ -534,8 +537,8 @@ def bond_statistics_batch(
     (``canonical_averages_dtype``), ``'finalized_canonical_averages'``
     (``finalized_canonical_averages_dtype``) and ``'number_of_runs'``.
 
-    Backend keyword arguments: ``rng`` (``'philox'`` default, or ``'mt19937'``
-    for numpy's stream bit for bit), ``device``, ``distributed`` (combine
+    Backend keyword arguments: ``rng`` (``'philox'`` default; ``'feistel'``, the
+    keyed-bijection throughput mode; or ``'mt19937'`` for numpy's stream bit for bit), ``device``, ``distributed`` (combine
     across ranks; default: whether ``torch.distributed`` is initialised).
     """
     from . import percolate as _percolate
@@ -544,7 +547,9 @@ def bond_statistics_batch(
     device = kwargs.get('device')
     ctx = _native.context_for(lowered, _default_device() if device is None else device)
     rng = kwargs.get('rng', 'philox')
-    mode = _native.PERM_PHILOX if rng == 'philox' else _native.PERM_MT19937
+    if rng not in _native.RNG_MODES:
+        raise ValueError("rng must be 'mt19937', 'philox' or 'feistel'")
+    mode = _native.RNG_MODES[rng]
     seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
     ps = np.ascontiguousarray(ps, dtype=np.float64)
 

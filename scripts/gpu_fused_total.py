@@ -10,11 +10,11 @@ ctx = _native.Context(0); ctx.set_graph(g)
 ctx.set_ps(np.linspace(0.45, 0.55, 100))
 seeds = np.arange(R, dtype=np.uint32)
 flags = _native.FUSE_MICRO | _native.FUSE_CANON
-ctx.run_fused(R, _native.PERM_PHILOX, seeds, flags)
+ctx.run_fused(R, _native.RNG_MODES[os.environ.get('PZ_RNG', 'philox')], seeds, flags)
 ctx.reset_accumulators(); ctx.synchronize()
 ctx.profile(True)
 ctx.timer_start(); t0 = time.time()
-ctx.run_fused(R, _native.PERM_PHILOX, seeds, flags)
+ctx.run_fused(R, _native.RNG_MODES[os.environ.get('PZ_RNG', 'philox')], seeds, flags)
 ms = ctx.timer_stop(); wall = time.time() - t0
 print("env PIPE=%s CLAIM=%s: L=%d R=%d device %.1f ms wall %.1f ms -> %.3g bonds/s" % (
     os.environ.get("PZ_PIPELINE"), os.environ.get("PZ_CLAIM_LOG2"), L, R, ms, wall * 1e3, R * g.num_edges / (ms * 1e-3)))

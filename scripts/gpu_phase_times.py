@@ -11,7 +11,7 @@ for L, R in cfg:
     M = g.num_edges
     seeds = np.arange(R, dtype=np.uint32)
     ctx.set_ps(np.linspace(0.45, 0.55, 100))
-    mode = _native.PERM_PHILOX
+    mode = _native.RNG_MODES[os.environ.get('PZ_RNG', 'philox')]
     flags = _native.FUSE_MICRO | _native.FUSE_CANON
     ctx.run_fused(min(R, 256), mode, seeds[:min(R, 256)], flags)   # warm-up
     ctx.reset_accumulators()

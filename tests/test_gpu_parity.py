@@ -426,6 +426,22 @@ def test_fused_hpc_batch_equals_reference_map_reduce():
         np.testing.assert_allclose(got[f], ref[f], rtol=1e-9, atol=1e-13 * scale)
 
 
+def test_feistel_bond_orders_match_restatement():
+    from pypercolate_b200 import lowering
+    from oracle import oracle
+    n = _native()
+    for g in (lowering.lowered_spanning_1d_chain(2), lowering.lowered_spanning_2d_grid(3),
+              lowering.lowered_spanning_2d_grid(8), lowering.lowered_spanning_2d_grid(32),
+              lowering.lowered_spanning_2d_grid(182), lowering.lowered_spanning_2d_grid(256),
+              lowering.lowered_spanning_3d_grid(20)):
+        ctx = ctx_for(g)
+        seeds = np.array([0, 1, 42, 2 ** 32 - 1, 99], dtype=np.uint32)
+        perms = ctx.make_perms(seeds.size, n.PERM_FEISTEL, seeds)
+        for r, s in enumerate(seeds):
+            assert np.array_equal(perms[r], oracle.feistel_permutation(int(s), g.num_edges)), (g.num_edges, s)
+        ctx.close()
+
+
 # ---------------------------------------------------------------------------
 # full-size properties (BASELINE configs 3-5): no oracle can walk these in bulk
 # ---------------------------------------------------------------------------
@@ -462,28 +478,30 @@ def test_full_size_invariants(kind, L, runs, check):
     ctx.close()
 
 
-def test_statistical_agreement_of_philox_mode():
-    """Philox bond orders are validated statistically: the spanning probability
-    at the 2D threshold from 2000 Philox runs must sit inside the reference
+@pytest.mark.parametrize("mode_name", ["PERM_PHILOX", "PERM_FEISTEL"])
+def test_statistical_agreement_of_philox_mode(mode_name):
+    """Device bond orders are validated statistically: the spanning probability
+    at the 2D threshold from 2000 runs must sit inside the reference
     stream's own 5-sigma binomial interval (and vice versa)."""
     from pypercolate_b200 import lowering
     n = _native()
     g = lowering.lowered_spanning_2d_grid(32)
     runs = 2000
     res = {}
-    for mode in (n.PERM_MT19937, n.PERM_PHILOX):
+    dev_mode = getattr(n, mode_name)
+    for mode in (n.PERM_MT19937, dev_mode):
         ctx = ctx_for(g)
         ctx.run_fused(runs, mode, np.arange(runs, dtype=np.uint32) + 1, n.FUSE_MICRO)
         mean, var = ctx.micro_finalize()
         res[mode] = (mean, var)
         ctx.close()
     for i in (g.num_edges // 2, int(0.45 * g.num_edges), int(0.55 * g.num_edges)):
-        k0, k1 = res[n.PERM_MT19937][0][0][i], res[n.PERM_PHILOX][0][0][i]
+        k0, k1 = res[n.PERM_MT19937][0][0][i], res[dev_mode][0][0][i]
         p = (k0 + k1) / (2 * runs)
         sigma = np.sqrt(2 * runs * p * (1 - p)) + 1.0
         assert abs(k0 - k1) < 5 * sigma
-        m0, m1 = res[n.PERM_MT19937][0][1][i], res[n.PERM_PHILOX][0][1][i]
-        s = np.sqrt((res[n.PERM_MT19937][1][0][i] + res[n.PERM_PHILOX][1][0][i]) / runs)
+        m0, m1 = res[n.PERM_MT19937][0][1][i], res[dev_mode][0][1][i]
+        s = np.sqrt((res[n.PERM_MT19937][1][0][i] + res[dev_mode][1][0][i]) / runs)
         assert abs(m0 - m1) < 5 * s
 
 
