@@ -8,7 +8,8 @@ L = 256 square lattice (BASELINE.json config 3: 1e5 runs, fused microcanonical
     python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm
 
 A step is one pass of the hot path over the whole batch of runs: bond orders
-(Philox, on the device) -> union-find sweep -> per-n exact sums over runs and
+(device RNG: the Philox-keyed Feistel bijection by default, `--rng philox` for the
+bucketed Philox Fisher-Yates) -> union-find sweep -> per-n exact sums over runs and
 per-run binomial contraction -> (multi-GPU) one NCCL exchange -> per-n mean /
 variance.  Strong scaling: the 1e5 runs are split over the ranks.
 
@@ -38,11 +39,19 @@ UNIT = "bond-additions/s"
 ALGO_BYTES_PER_BOND = 20.0 + 8.0 * (L * L - 1) / (2 * L * (L - 1))
 
 
-def workload_config(n_gpus, runs_total):
+RNG_TEXT = {
+    "feistel": "bond orders on device = Philox-keyed 20-round Feistel bijection with cycle walking",
+    "philox": "bond orders on device = Philox4x32-10 bucketed Fisher-Yates",
+    "mt19937": "bond orders on device = numpy RandomState(seed).permutation stream, bit for bit",
+}
+
+
+def workload_config(n_gpus, runs_total, rng="feistel"):
     return {
-        "workload": "spanning_2d_grid L=256 (N=65536, M=130560), %d runs total, Philox bond orders "
-                    "on device, fused microcanonical sums + per-run canonical contraction at "
-                    "%d p in [0.45, 0.55]" % (runs_total, NUM_P),
+        "workload": "spanning_2d_grid L=256 (N=65536, M=130560), %d runs total, %s, "
+                    "fused microcanonical sums + per-run canonical contraction at "
+                    "%d p in [0.45, 0.55]" % (runs_total, RNG_TEXT[rng], NUM_P),
+        "rng": rng,
         "runs_total": runs_total,
         "runs_per_gpu": runs_total // n_gpus,
         "num_p": NUM_P,
@@ -167,6 +176,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--runs", type=int, default=TOTAL_RUNS, help="total runs per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rng", default="feistel", choices=["feistel", "philox", "mt19937"],
+                    help="device bond-order generator of our arm")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -204,7 +215,7 @@ def main():
     seeds_host = (np.arange(lo, hi, dtype=np.uint64) * 2654435761 % (2 ** 32)).astype(np.uint32)
     seeds_dev = torch.from_numpy(seeds_host.view(np.int32)).cuda()
     flags = _native.FUSE_MICRO | _native.FUSE_CANON
-    mode = _native.PERM_PHILOX | _native.SEEDS_ON_DEVICE
+    mode = _native.RNG_MODES[args.rng] | _native.SEEDS_ON_DEVICE
 
     def step_device():
         """inputs (graph, seeds, binomial weights) resident in HBM"""
@@ -217,7 +228,7 @@ def main():
     def step_e2e():
         """the public call: host seeds / ps in, host statistics out"""
         return hpc.bond_statistics_batch(g, N, M, seeds_host, ps, 0.3173, device=local,
-                                         rng='philox', distributed=world > 1)
+                                         rng=args.rng, distributed=world > 1)
 
     # ---- device-resident throughput -------------------------------------------
     for _ in range(args.warmup):
@@ -275,10 +286,10 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": workload_config(world, args.runs),
+            "config": workload_config(world, args.runs, args.rng),
             "runs_per_s": float(args.runs) * args.steps / (ms * 1e-3),
             "roofline": {
-                "bound": "hbm", "kernel": "sweep_kernel (union-find, shared-memory latency bound)",
+                "bound": "hbm", "kernel": "sweep_cta_kernel (union-find; shared-memory latency bound, see DESIGN.md)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_bond": ALGO_BYTES_PER_BOND,

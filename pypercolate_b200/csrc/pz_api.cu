@@ -83,7 +83,10 @@ struct pz_ctx {
     static constexpr int PZ_SLOTS = 3;
     Slot slots[PZ_SLOTS];
     cudaStream_t s_perm = nullptr, s_stats = nullptr;
-    int pipeline = 0;                     // PZ_PIPELINE=1: bond orders / sweep / statistics on three streams
+    int pipeline = -1;                    // PZ_PIPELINE: 0 one stream; 1 bond orders / sweep / statistics on
+                                          // three streams; 2 only the bond orders overlap the sweep;
+                                          // -1 (default): 2 for the Feistel mode (no shared memory, pure ALU:
+                                          // it fits next to a resident sweep CTA), else 0
     DevBuf<uint32_t> gscratch;
     DevBuf<uint8_t> rows;
 
@@ -92,7 +95,8 @@ struct pz_ctx {
     DevBuf<unsigned long long> span_cum;  // M + 1
     DevBuf<double> fin;                   // 13 * (M+1): mean[7], var[6]
     int64_t micro_runs = 0;
-    int ckpt_every = 1024;                // run state checkpoints every so many rows
+    int ckpt_every = 64;                  // run state checkpoints every so many rows (64 = tile
+                                          // form of accumulate; PZ_CKPT_EVERY=1024: segment form)
 
     // canonical
     int32_t num_p = 0;
@@ -155,6 +159,8 @@ static void collect_phases(pz_ctx *c)
 namespace pz {
 cudaError_t launch_checkpoints(const StatsArgs &a, RunState *ckpt, int every, int n_ckpt,
                                cudaStream_t s);
+cudaError_t launch_accumulate_tiles(const StatsArgs &a, unsigned long long *acc, const RunState *ckpt,
+                                    int every, int n_ckpt, cudaStream_t s);
 cudaError_t launch_accumulate(const StatsArgs &a, unsigned long long *acc, const RunState *ckpt,
                               int seg, int n_ckpt, cudaStream_t s);
 cudaError_t launch_micro_finalize(int32_t N, int32_t M, int64_t runs, const unsigned long long *acc,
@@ -214,6 +220,7 @@ int pz_create(int device, pz_ctx **out)
     if (const char *e = getenv("PZ_SWEEP_TEAM")) c->team = atoi(e);
     if (const char *e = getenv("PZ_CLAIM_LOG2")) c->claim_cap = atoi(e);
     if (const char *e = getenv("PZ_CTA_WARPS")) c->cta_warps = atoi(e);
+    if (const char *e = getenv("PZ_CKPT_EVERY")) c->ckpt_every = atoi(e) == 64 ? 64 : 1024;
     if (const char *e = getenv("PZ_CHUNK_BYTES")) c->chunk_bytes = (size_t)atoll(e);
     *out = c;
     return PZ_OK;
@@ -560,17 +567,22 @@ int pz_run_fused(pz_ctx *c, int32_t R, int perm_mode, const void *perm_src, int 
     // be visible to the side streams
     PZ_CUDA(cudaStreamSynchronize(c->stream));
     const int P = c->num_p;
-    const int nslot = c->pipeline ? pz_ctx::PZ_SLOTS : 1;
-    const size_t per_run = (size_t)std::max(c->M, 1) * 12 + 4096;   // orders + widest records + checkpoints
+    const int pipeline = c->pipeline >= 0 ? c->pipeline
+                         : ((perm_mode & ~PZ_SEEDS_ON_DEVICE) == PZ_PERM_FEISTEL ? 2 : 0);
+    const int nslot = pipeline ? pz_ctx::PZ_SLOTS : 1;
+    const size_t per_run = (size_t)std::max(c->M, 1) * 12 + 4096 +   // orders + widest records
+                           ((size_t)c->M / c->ckpt_every + 1) * 32;  // + checkpoints
     size_t chunk = std::max<size_t>(1, (c->chunk_bytes / pz_ctx::PZ_SLOTS) / per_run);
     // at least a few chunks so that the streams overlap, but never below 4 waves of runs
     if (nslot > 1) {
         const size_t want = std::max<size_t>((size_t)c->sms * 4, ((size_t)R + 2 * nslot - 1) / (2 * nslot));
         chunk = std::min(chunk, want);
     }
+    // whole waves of sweep CTAs (one run per CTA, grid = a multiple of the SM count)
+    if (chunk > (size_t)c->sms) chunk -= chunk % (size_t)c->sms;
     const int n_ckpt = c->M / c->ckpt_every + 1;
-    cudaStream_t sp = c->pipeline ? c->s_perm : c->stream;
-    cudaStream_t ss = c->pipeline == 1 ? c->s_stats : c->stream;    // 2: only the bond orders overlap
+    cudaStream_t sp = pipeline ? c->s_perm : c->stream;
+    cudaStream_t ss = pipeline == 1 ? c->s_stats : c->stream;    // 2: only the bond orders overlap
     size_t ci = 0;
     for (size_t r0 = 0; r0 < (size_t)R; r0 += chunk, ++ci) {
         const int32_t n = (int32_t)std::min(chunk, (size_t)R - r0);
@@ -592,7 +604,10 @@ int pz_run_fused(pz_ctx *c, int32_t R, int perm_mode, const void *perm_src, int 
         c->launches += 1;
         if (flags & PZ_FUSE_MICRO) {
             PhaseTimer t(c, PZ_PHASE_ACCUM, ss);
-            PZ_CUDA(launch_accumulate(ch.stats, c->acc.p, sl.ckpt.p, c->ckpt_every, n_ckpt, ss));
+            if (c->ckpt_every == 64)
+                PZ_CUDA(launch_accumulate_tiles(ch.stats, c->acc.p, sl.ckpt.p, c->ckpt_every, n_ckpt, ss));
+            else
+                PZ_CUDA(launch_accumulate(ch.stats, c->acc.p, sl.ckpt.p, c->ckpt_every, n_ckpt, ss));
             c->launches += 1;
             c->micro_runs += n;
         }

@@ -341,6 +341,169 @@ cudaError_t launch_accumulate(const StatsArgs &a, unsigned long long *acc, const
 }
 
 // ===========================================================================
+// accumulate, tile form (the one the fused path uses): one LANE owns two
+// consecutive rows of a 64-row tile, one warp walks the runs of a group for that
+// tile.  Per run: two coalesced record loads per lane, one broadcast load of the
+// run state at the tile boundary (checkpoint every 64 rows), a warp scan of the
+// 2-row deltas, then the row statistics are added to REGISTER accumulators
+// (carry chains, 64/128/192 bits).  Only after the last run of the group are
+// the totals split into the 32-bit-limb words of the accumulator block and
+// added with one 64-bit atomic per (row, word) -- no shared memory, no per-run
+// exchange between lanes beyond the scan.
+// ===========================================================================
+static constexpr int ACC_TILE = 64;            // rows per warp tile = checkpoint spacing
+static constexpr int ACC_GROUP = 512;          // runs per warp
+
+struct U128 { uint64_t lo, hi; };
+struct U192 { uint64_t w0, w1, w2; };
+__device__ __forceinline__ void add128(U128 &a, uint64_t b) {
+    asm("add.cc.u64 %0, %0, %2;\n\taddc.u64 %1, %1, 0;" : "+l"(a.lo), "+l"(a.hi) : "l"(b));
+}
+__device__ __forceinline__ void add192(U192 &a, uint64_t blo, uint64_t bhi) {
+    asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u64 %2, %2, 0;"
+        : "+l"(a.w0), "+l"(a.w1), "+l"(a.w2) : "l"(blo), "l"(bhi));
+}
+
+struct RowAcc {
+    uint64_t mx, c;            // sum max, sum c          (< 2^29 * runs of a group)
+    U128 mx2, c2;              // sum max^2, sum c^2
+    U128 m[3];                 // sum moments[2..4]
+    U192 mm[3];                // sum moments[2..4]^2
+    __device__ __forceinline__ void clear() {
+        mx = c = 0; mx2 = c2 = U128{0, 0};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { m[k] = U128{0, 0}; mm[k] = U192{0, 0, 0}; }
+    }
+    __device__ __forceinline__ void add(uint32_t sc, uint32_t smx, uint64_t s2, uint64_t s3, uint64_t s4) {
+        const uint64_t x = smx, x2 = x * x, cc = sc;
+        mx += x; c += cc;
+        add128(mx2, x2);
+        add128(c2, cc * cc);
+        const uint64_t v[3] = {s2 - x2, s3 - x2 * x, s4 - x2 * x2};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            add128(m[k], v[k]);
+            add192(mm[k], v[k] * v[k], __umul64hi(v[k], v[k]));
+        }
+    }
+    // split into the limb words of the accumulator block and add them
+    __device__ __forceinline__ void flush(unsigned long long *w) const {
+        auto put = [&](int i, uint64_t v) { if (v) atomicAdd(&w[i], (unsigned long long)v); };
+        put(1, mx);
+        put(2, mx2.lo & 0xffffffffu); put(3, (mx2.lo >> 32) | (mx2.hi << 32));
+        put(4, c);
+        put(5, c2.lo & 0xffffffffu); put(6, (c2.lo >> 32) | (c2.hi << 32));
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            put(7 + 6 * k + 0, m[k].lo & 0xffffffffu);
+            put(7 + 6 * k + 1, (m[k].lo >> 32) | (m[k].hi << 32));
+            put(7 + 6 * k + 2, mm[k].w0 & 0xffffffffu);
+            put(7 + 6 * k + 3, mm[k].w0 >> 32);
+            put(7 + 6 * k + 4, mm[k].w1 & 0xffffffffu);
+            put(7 + 6 * k + 5, (mm[k].w1 >> 32) | (mm[k].w2 << 32));
+        }
+    }
+};
+
+template <class RecT>
+__global__ void __launch_bounds__(128, 3) accumulate_tiles_kernel(StatsArgs a, unsigned long long *acc,
+                                                                  const RunState *ckpt, int n_ckpt,
+                                                                  int n_tiles)
+{
+    const int lane = threadIdx.x & 31;
+    const long long wid = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int tile = (int)(wid % n_tiles);
+    const int run_lo = (int)(wid / n_tiles) * ACC_GROUP;
+    if (run_lo >= a.R) return;
+    const int run_hi = min(a.R, run_lo + ACC_GROUP);
+    const int M = a.M;
+    const RecT *recs = reinterpret_cast<const RecT *>(a.recs);
+    // this lane: records i0, i0 + 1 -> rows i0 + 1, i0 + 2
+    const int i0 = tile * ACC_TILE + 2 * lane;
+    const bool v0 = i0 < M, v1 = i0 + 1 < M;
+
+    if (tile == 0) {
+        if (a.spanning)
+            for (int r = run_lo + lane; r < run_hi; r += 32) {
+                const uint32_t ns = a.nspan[r];
+                if (ns != NSPAN_NEVER) atomicAdd(&acc[(size_t)ns * ACC_WORDS + 0], 1ull);
+            }
+        if (lane == 0) {
+            // row 0 is the same for every run (max = 1, c = 0, moments = N - 1):
+            // limb * count is exact in the limb-word format
+            const unsigned long long cnt = (unsigned long long)(run_hi - run_lo);
+            const uint64_t v = (uint64_t)a.N - 1, vv = v * v;
+            atomicAdd(&acc[1], cnt);
+            atomicAdd(&acc[2], cnt);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                atomicAdd(&acc[7 + 6 * k + 0], (unsigned long long)(v & 0xffffffffu) * cnt);
+                atomicAdd(&acc[7 + 6 * k + 1], (unsigned long long)(v >> 32) * cnt);
+                atomicAdd(&acc[7 + 6 * k + 2], (unsigned long long)(vv & 0xffffffffu) * cnt);
+                atomicAdd(&acc[7 + 6 * k + 3], (unsigned long long)(vv >> 32) * cnt);
+            }
+        }
+    }
+
+    RowAcc A, B;
+    A.clear(); B.clear();
+
+    auto load = [&](int run, RecT &r0, RecT &r1, RunState &st) {
+        const RecT *p = recs + (size_t)run * M + i0;
+        r0 = v0 ? __ldcs(p) : (RecT)0;
+        r1 = v1 ? __ldcs(p + 1) : (RecT)0;
+        const uint4 *q = reinterpret_cast<const uint4 *>(ckpt + (size_t)run * n_ckpt + tile);
+        const uint4 lo = __ldg(q), hi = __ldg(q + 1);
+        st.c = lo.x; st.mx = lo.y;
+        st.s2 = ((uint64_t)lo.w << 32) | lo.z;
+        st.s3 = ((uint64_t)hi.y << 32) | hi.x;
+        st.s4 = ((uint64_t)hi.w << 32) | hi.z;
+    };
+
+    RecT n0 = 0, n1 = 0;
+    RunState nst;
+    nst.init((uint32_t)a.N);
+    load(run_lo, n0, n1, nst);
+    for (int run = run_lo; run < run_hi; ++run) {
+        const RecT r0 = n0, r1 = n1;
+        const RunState base = nst;
+        if (run + 1 < run_hi) load(run + 1, n0, n1, nst);      // prefetch the next run
+
+        const Delta d0 = delta_of<RecT>(r0), d1 = delta_of<RecT>(r1);
+        Delta d = delta_combine(d0, d1);
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) {
+            const Delta o = delta_shfl_up(d, k);
+            if (lane >= k) d = delta_combine(o, d);
+        }
+        Delta ex = delta_shfl_up(d, 1);                        // exclusive prefix of this lane
+        if (lane == 0) ex = Delta{0, 0, 0, 0, 0};
+        // state after row i0 + 1
+        const uint32_t ca = base.c + ex.c + d0.c;
+        const uint32_t xa = max(max(base.mx, ex.mx), d0.mx);
+        const uint64_t s2a = base.s2 + ex.s2 + d0.s2, s3a = base.s3 + ex.s3 + d0.s3,
+                       s4a = base.s4 + ex.s4 + d0.s4;
+        if (v0) A.add(ca, xa, s2a, s3a, s4a);
+        if (v1) B.add(ca + d1.c, max(xa, d1.mx), s2a + d1.s2, s3a + d1.s3, s4a + d1.s4);
+    }
+    if (v0) A.flush(acc + (size_t)(i0 + 1) * ACC_WORDS);
+    if (v1) B.flush(acc + (size_t)(i0 + 2) * ACC_WORDS);
+}
+
+cudaError_t launch_accumulate_tiles(const StatsArgs &a, unsigned long long *acc, const RunState *ckpt,
+                                    int every, int n_ckpt, cudaStream_t s)
+{
+    if (a.R <= 0) return cudaSuccess;
+    if (every != ACC_TILE) return cudaErrorInvalidValue;
+    const int n_tiles = a.M > 0 ? (a.M + ACC_TILE - 1) / ACC_TILE : 1;
+    const long long warps = (long long)((a.R + ACC_GROUP - 1) / ACC_GROUP) * n_tiles;
+    const int grid = (int)((warps + 3) / 4);
+    if (a.rec64) accumulate_tiles_kernel<uint64_t><<<grid, 128, 0, s>>>(a, acc, ckpt, n_ckpt, n_tiles);
+    else accumulate_tiles_kernel<uint32_t><<<grid, 128, 0, s>>>(a, acc, ckpt, n_ckpt, n_tiles);
+    return cudaGetLastError();
+}
+
+// ===========================================================================
 // micro_finalize: exact sums -> float64 mean and unbiased variance per n.
 // var = (R * sum x^2 - (sum x)^2) / (R (R-1)) is formed in 256-bit integer
 // arithmetic, so it is exactly 0 when all runs agree (the reference's

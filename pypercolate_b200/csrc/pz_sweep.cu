@@ -23,6 +23,7 @@
 // otherwise in a per-warp slab of global memory that stays L2-resident.
 // Output per bond is one merge record (see pz_common.cuh); per run one word,
 // the first n at which the two spanning sides are joined (hpc.py:269-274).
+#include <cstdio>
 #include "pz_common.cuh"
 #include "pz_internal.h"
 
@@ -484,6 +485,12 @@ __global__ void __launch_bounds__(32 * CTA_WARPS, 1) sweep_cta_kernel(SweepArgs 
         Rec *rec_out = reinterpret_cast<Rec *>(a.recs) + (size_t)run * M;
         bool track = spanning;                 // CTA-uniform
         uint32_t epoch = 0x003fffffu;          // decreasing: newer claims always win over stale ones
+#ifdef PZ_TIMING
+        long long tm_find = 0, tm_init = clock64(), tm_rounds = 0, tm_t = 0, tm_seg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tm_p = 0, tm_star = 0;
+#define TM(k) { const long long _c = clock64(); tm_seg[k] += _c - tm_p; tm_p = _c; }
+#else
+#define TM(k)
+#endif
 
         // two-deep software pipeline: perm[n] -> edges[perm[n]] -> use
         Edge uv_next = Edge();
@@ -499,13 +506,25 @@ __global__ void __launch_bounds__(32 * CTA_WARPS, 1) sweep_cta_kernel(SweepArgs 
             if (n + 2 * CTA_THREADS < M) e_next = __ldcs(&perm[n + 2 * CTA_THREADS]);
 
             uint32_t ru = 0, rv = 0, tu = 0, tv = 0;
+#ifdef PZ_TIMING
+            tm_t = clock64();
+#endif
             if (valid) {
                 edge_uv(uv, ru, rv);
                 st.find_pair(ru, rv, tu, tv);
             }
             bool pending = valid && ru != rv;
             Rec rec = 0;
+#ifdef PZ_TIMING
+            tm_find += clock64() - tm_t;
+            tm_p = clock64();
+            __syncthreads();
+            TM(7)
+#endif
             for (;;) {
+#ifdef PZ_TIMING
+                ++tm_rounds; tm_p = clock64();
+#endif
                 // a warp without pending bonds only takes part in the barriers
                 const bool warp_has = __any_sync(0xffffffffu, pending);
                 const uint32_t key = (epoch << 10) | (uint32_t)tid;
@@ -524,13 +543,17 @@ __global__ void __launch_bounds__(32 * CTA_WARPS, 1) sweep_cta_kernel(SweepArgs 
                         if (!star) atomicMin(&claim[sv], key);
                     }
                 }
+                TM(0)
                 if (!__syncthreads_or(pending)) break;          // nothing (left) to merge
+                TM(1)
                 bool own = false;
                 if (warp_has) {
                     own = pending && claim[su] == key && claim[sv] == key;
                     if (pending && !own) atomicMin(&sh->bmin, (uint32_t)tid);
                 }
+                TM(2)
                 const int nstar = __syncthreads_count(own && star);
+                TM(3)
                 bool won = false;
                 if (own && !star) {
                     rec = make_rec<Rec>(Store::size_m1(tu), Store::size_m1(tv));
@@ -542,6 +565,10 @@ __global__ void __launch_bounds__(32 * CTA_WARPS, 1) sweep_cta_kernel(SweepArgs 
                     if (hk > sh->hub_key) atomicMax(&sh->hub_key, hk);
                     won = true;
                 }
+                TM(4)
+#ifdef PZ_TIMING
+                if (nstar) ++tm_star;
+#endif
                 if (nstar) {
                     // star bonds merge together iff no earlier bond of the batch is blocked
                     const bool sw = own && star && (uint32_t)tid < sh->bmin;
@@ -590,19 +617,28 @@ __global__ void __launch_bounds__(32 * CTA_WARPS, 1) sweep_cta_kernel(SweepArgs 
                         won = true;
                     }
                 }
+                TM(5)
                 if (won) pending = false;
                 --epoch;
                 if (tid == 0) sh->bmin = 0xffffffffu;           // read only between the two barriers above
                 if (!__syncthreads_or(pending)) break;          // every candidate merged
+                TM(6)
                 if (pending) {                                  // walk up to the new roots
                     st.find2(ru, rv, tu, tv);
                     pending = ru != rv;
                 }
+                TM(7)
             }
             if (track && sh->span_min != NSPAN_NEVER) track = false;
             if (valid) __stcs(&rec_out[n], rec);
         }
         __syncthreads();
+#ifdef PZ_TIMING
+        if ((tid & 127) == 0 && blockIdx.x == 0 && run < (int)gridDim.x)
+            printf("warp %2d: total %lld find %lld (%lld iterations, %lld star) claim %lld bar1 %lld own %lld bar2 %lld merge %lld star %lld bar3 %lld find2+findbar %lld\n",
+                   warp, clock64() - tm_init, tm_find, tm_rounds, tm_star,
+                   tm_seg[0], tm_seg[1], tm_seg[2], tm_seg[3], tm_seg[4], tm_seg[5], tm_seg[6], tm_seg[7]);
+#endif
         if (tid == 0) a.nspan[run] = sh->span_min;
         __syncthreads();
     }

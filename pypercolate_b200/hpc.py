@@ -498,7 +498,10 @@ def bond_canonical_averages_batch(
     binomial weights of every ``p`` (hpc.py:488-515) and folded into
     ``(number_of_runs, mean, M2)`` (hpc.py:607-702) without leaving the GPU.
     Returns an array of ``canonical_averages_dtype`` ready for
-    ``finalize_canonical_averages`` or further ``bond_reduce``."""
+    ``finalize_canonical_averages`` or further ``bond_reduce``.
+    Backend keyword arguments: ``rng`` (``'mt19937'`` default, ``'philox'``,
+    ``'feistel'``), ``device``, ``distributed`` (``seeds`` is this rank's shard;
+    combine the partials of all ranks of ``torch.distributed``)."""
     lowered = _lower(perc_graph, spanning_cluster, auxiliary_node_attributes,
                      auxiliary_edge_attributes, spanning_sides)
     device = kwargs.get('device')
@@ -510,6 +513,10 @@ def bond_canonical_averages_batch(
     if rng not in _native.RNG_MODES:
         raise ValueError("rng must be 'mt19937', 'philox' or 'feistel'")
     ctx.run_fused(seeds.size, _native.RNG_MODES[rng], seeds, _native.FUSE_CANON)
+    if kwargs.get('distributed'):
+        # ``seeds`` is this rank's shard: fold the partials of all ranks (rank order)
+        from . import multi
+        multi.allreduce_context(ctx)
     count, mean, m2 = ctx.canon_export()
     return _canonical_averages_from_partials(count, mean, m2, spanning_cluster)
 

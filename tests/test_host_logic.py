@@ -177,3 +177,22 @@ def test_spanning_graph_builders():
     assert sum(1 for *_, a in g.edges(data=True) if 'span' in a) == 6
     c = percolate.spanning_1d_chain(4)
     assert c.number_of_nodes() == 6 and c.nodes[0]['span'] == 0 and c.nodes[5]['span'] == 1
+
+
+def test_study_seed_recipe_and_disk_format(tmp_path):
+    """The study driver draws seeds like percolate/share/jugfile.py:36-37,172,215 and
+    appends one dataset per system size, refusing to overwrite (jugfile.py:138-156)."""
+    from pypercolate_b200 import study
+    assert study.DEFAULT_SEED == 201508061904 % 4294967296
+    seeds = study.study_seeds((8, 16, 32), 100)
+    rng = np.random.RandomState(seed=study.DEFAULT_SEED)
+    for L in (8, 16, 32):
+        assert np.array_equal(seeds[L], rng.randint(4294967296, size=100))
+    path = str(tmp_path / "out.npz")
+    a = np.arange(6, dtype=np.float64).reshape(2, 3)
+    study.write_to_disk(path, 8, a)
+    study.write_to_disk(path, 16, a * 2)
+    with np.load(path) as z:
+        assert sorted(z.files) == ['16', '8'] and np.array_equal(z['16'], a * 2)
+    with pytest.raises(RuntimeError):
+        study.write_to_disk(path, 8, a)
