@@ -578,8 +578,8 @@ int pz_run_fused(pz_ctx *c, int32_t R, int perm_mode, const void *perm_src, int 
         const size_t want = std::max<size_t>((size_t)c->sms * 4, ((size_t)R + 2 * nslot - 1) / (2 * nslot));
         chunk = std::min(chunk, want);
     }
-    // whole waves of sweep CTAs (one run per CTA, grid = a multiple of the SM count)
-    if (chunk > (size_t)c->sms) chunk -= chunk % (size_t)c->sms;
+    // several chunks: whole waves of sweep CTAs per chunk (grid = a multiple of the SM count)
+    if ((size_t)R > chunk && chunk > (size_t)c->sms) chunk -= chunk % (size_t)c->sms;
     const int n_ckpt = c->M / c->ckpt_every + 1;
     cudaStream_t sp = pipeline ? c->s_perm : c->stream;
     cudaStream_t ss = pipeline == 1 ? c->s_stats : c->stream;    // 2: only the bond orders overlap
@@ -709,18 +709,32 @@ int pz_set_ps(pz_ctx *c, int32_t M, int32_t num_p, const double *ps, double *pmf
     for (int i = 0; i < num_p; ++i)
         if (!(ps[i] >= 0.0 && ps[i] <= 1.0)) return fail(PZ_ERR_ARG, "pz_set_ps: p must lie in [0, 1]");
     PZ_CUDA(cudaSetDevice(c->device));
+    const bool want_sf = c->N > 0 && M == c->M;      // only the fused path needs the table
+    // same table as last time (a study calls this once per batch of seeds): keep it
+    const bool cached = num_p > 0 && c->num_p == num_p && c->pmf_M == M &&
+                        std::equal(ps, ps + num_p, c->ps.begin()) &&
+                        (!want_sf || c->sf_M == M) && c->pmf.p != nullptr;
     c->num_p = num_p;
     c->pmf_M = M;
     c->ps.assign(ps, ps + num_p);
     c->canon_count = 0; c->canon_last_R = 0;
     if (num_p == 0) return PZ_OK;
+    const size_t S = (size_t)M + 1;
+    if (cached) {
+        if (pmf_out) {
+            for (int i = 0; i < num_p; ++i)
+                PZ_CUDA(cudaMemcpyAsync(pmf_out + (size_t)c->porder[i] * S, c->pmf.p + (size_t)i * S, S * 8,
+                                        cudaMemcpyDeviceToHost, c->stream));
+            PZ_CUDA(cudaStreamSynchronize(c->stream));
+        }
+        return PZ_OK;
+    }
     c->porder.resize(num_p);
     for (int i = 0; i < num_p; ++i) c->porder[i] = i;
     std::stable_sort(c->porder.begin(), c->porder.end(),
                      [&](int a, int b) { return ps[a] < ps[b]; });
     std::vector<double> sorted(num_p);
     for (int i = 0; i < num_p; ++i) sorted[i] = ps[c->porder[i]];
-    const size_t S = (size_t)M + 1;
     PZ_CUDA(c->ps_dev.ensure(num_p));
     PZ_CUDA(c->pmf.ensure((size_t)num_p * S));
     PZ_CUDA(c->band_lo.ensure(num_p));
@@ -728,7 +742,6 @@ int pz_set_ps(pz_ctx *c, int32_t M, int32_t num_p, const double *ps, double *pmf
     PZ_CUDA(c->tband_lo.ensure(num_p));
     PZ_CUDA(c->tband_hi.ensure(num_p));
     PZ_CUDA(c->canon_flags.ensure(num_p));
-    const bool want_sf = c->N > 0 && M == c->M;      // only the fused path needs the table
     if (want_sf) PZ_CUDA(c->sf.ensure((size_t)num_p * S));
     PZ_CUDA(c->porder_dev.ensure(num_p));
     PZ_CUDA(cudaMemcpyAsync(c->ps_dev.p, sorted.data(), (size_t)num_p * 8, cudaMemcpyHostToDevice, c->stream));

@@ -27,9 +27,10 @@
 //    bond pi_seed(n), evaluated independently per position -- no scatter, no
 //    atomics, no shared memory, one coalesced write.  pi is an alternating
 //    unbalanced Feistel network over the 2^k >= M points (k = ceil(log2 M),
-//    halves of k/2 and k - k/2 bits that swap roles every round), 20 rounds,
-//    round function = both words of the 64-bit product (R ^ key_i) * 0xD2511F53
-//    xor-ed together (the Philox multiplier), round keys = Philox4x32-10 words of
+//    halves of k/2 and k - k/2 bits that swap roles every round), 20 rounds:
+//    with R = the low k - k/2 bits and L = the rest, f = hi ^ lo of the 64-bit
+//    product (R ^ key_i) * 0xD2511F53 (the Philox multiplier),
+//    x' = R << (k/2) | (L ^ f[k - k/2 .. k)); round keys = Philox4x32-10 words of
 //    counter (i >> 2, 0, 0, 3) under key (seed, 'PERC'); points that land at or
 //    above M are walked on (cycle walking) until they fall below M, which keeps
 //    the map a bijection of [0, M).  A pseudo-random permutation family rather
@@ -293,25 +294,36 @@ __global__ void __launch_bounds__(FE_THREADS) perm_feistel_kernel(int32_t M, int
     for (int i = 0; i < FEISTEL_ROUNDS; ++i) key[i] = keys[i];
 
     const int a = k_bits >> 1, b = k_bits - a;
-    const uint32_t mb = (1u << b) - 1u;
-    const int sh = 32 - a;
+    const uint32_t mb = (1u << b) - 1u;            // right half
+    const uint32_t mba = mb << a;                  // where the right half goes
+    const uint32_t mk = k_bits >= 32 ? 0xffffffffu : (1u << k_bits) - 1u;
+    const uint32_t two_a = 1u << a, two_32mb = 1u << (32 - b);
     int32_t *out = perms + (size_t)run * M;
     const int base = blockIdx.x * (FE_THREADS * FE_ITEMS) + threadIdx.x;
+    // every lane walks its own list of positions: a point that lands at or above M
+    // is walked on by that lane alone (no lane waits for another lane's walk)
+    int n = base;
+    const int n_end = min(M, base + FE_ITEMS * FE_THREADS);
+    uint32_t x = (uint32_t)n;
+    while (n < n_end) {
 #pragma unroll
-    for (int j = 0; j < FE_ITEMS; ++j) {
-        const int n = base + j * FE_THREADS;
-        if (n >= M) break;
-        uint32_t x = (uint32_t)n;
-        do {
-#pragma unroll
-            for (int i = 0; i < FEISTEL_ROUNDS; ++i) {
-                const uint32_t r = x & mb;
-                const uint64_t pr = (uint64_t)(r ^ key[i]) * 0xD2511F53u;
-                const uint32_t f = (uint32_t)(pr >> 32) ^ (uint32_t)pr;
-                x = (r << a) | ((x >> b) ^ (f >> sh));
-            }
-        } while (x >= (uint32_t)M);
-        out[n] = (int32_t)x;
+        for (int i = 0; i < FEISTEL_ROUNDS; ++i) {
+            // bits above k carry garbage between rounds; no round reads them
+            const uint64_t pr = (uint64_t)((x & mb) ^ key[i]) * 0xD2511F53u;
+            const uint32_t y = x ^ (uint32_t)(pr >> 32) ^ (uint32_t)pr;
+            // both shifts as multiplies (x << a = x * 2^a, y >> b = hi(y * 2^(32-b))): the
+            // integer-multiply pipe is idle otherwise and the logic pipe is the bound
+            uint32_t xa, s;
+            asm("mul.lo.u32 %0, %1, %2;" : "=r"(xa) : "r"(x), "r"(two_a));
+            asm("mul.hi.u32 %0, %1, %2;" : "=r"(s) : "r"(y), "r"(two_32mb));
+            x = (xa & mba) | (s & ~mba);
+        }
+        x &= mk;
+        if (x < (uint32_t)M) {
+            out[n] = (int32_t)x;
+            n += FE_THREADS;
+            x = (uint32_t)n;
+        }
     }
 }
 

@@ -39,12 +39,28 @@ def study_seeds(system_dimensions, number_of_runs, seed=DEFAULT_SEED):
             for L in system_dimensions}
 
 
+def _plain_names(array):
+    """Same memory layout, field names as plain ``str`` (the reference builds its
+    dtypes with ``np.str_`` keys, percolate/hpc.py:22-31, which NumPy 2 cannot
+    round-trip through the .npy header)."""
+    array = np.ascontiguousarray(array)
+    dt = array.dtype
+    if dt.names is None:
+        return array
+    plain = np.dtype({'names': [str(n) for n in dt.names],
+                      'formats': [dt.fields[n][0] for n in dt.names],
+                      'offsets': [dt.fields[n][1] for n in dt.names],
+                      'itemsize': dt.itemsize})
+    return array.view(plain)
+
+
 def write_to_disk(path, dimension, canonical_averages):
     """Append the finalised averages of one size (jugfile.py:138-156): an HDF5
     dataset named ``str(dimension)`` when h5py is importable and ``path`` ends
     in .h5/.hdf5, else an ``.npz`` archive with the same key.  Like the
     reference, an existing key is an error."""
     key = '{}'.format(dimension)
+    canonical_averages = _plain_names(canonical_averages)
     if path.endswith(('.h5', '.hdf5')):
         try:
             import h5py

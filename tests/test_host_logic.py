@@ -196,3 +196,9 @@ def test_study_seed_recipe_and_disk_format(tmp_path):
         assert sorted(z.files) == ['16', '8'] and np.array_equal(z['16'], a * 2)
     with pytest.raises(RuntimeError):
         study.write_to_disk(path, 8, a)
+    # the reference's dtypes carry np.str_ field names (percolate/hpc.py:22-31)
+    b = np.zeros(3, dtype=hpc.finalized_canonical_averages_dtype(True))
+    b['p'] = [0.1, 0.2, 0.3]
+    study.write_to_disk(path, 32, b)
+    with np.load(path) as z:
+        assert z['32'].dtype == b.dtype and np.array_equal(z['32'], b)
