@@ -165,7 +165,17 @@ def run_reference(args, rank, world):
                 "cannot travel to the GPU box; this arm times the C restatement of its algorithm "
                 "(oracle/pz_oracle.c) on all host cores",
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the real stdout."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+# everything else a library may print (NCCL's version banner goes to fd 1) lands on stderr
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 
 def main():
@@ -317,7 +327,7 @@ def main():
             }
         # sanity of the last e2e result (not timed)
         assert res["number_of_runs"] == args.runs
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -53,7 +53,8 @@ struct pz_ctx {
     int team = 1;             // CTA lock-step kernel (PZ_SWEEP_TEAM=0: single-warp A/B kernel)
     int claim_cap = 0;        // log2 of the largest claim table (PZ_CLAIM_LOG2; 0 = automatic)
     int cta_warps = 0;        // warps of a sweep CTA = bonds per batch / 32 (PZ_CTA_WARPS; 0 = automatic)
-    size_t chunk_bytes = (size_t)24 << 30;      // total scratch budget of the slots
+    size_t chunk_bytes = (size_t)24 << 30;      // total scratch budget of the slots (pz_create: half of
+                                                // the free device memory, at most 72 GiB; PZ_CHUNK_BYTES)
 
     // graph
     int32_t N = 0, M = 0;
@@ -221,6 +222,11 @@ int pz_create(int device, pz_ctx **out)
     if (const char *e = getenv("PZ_CLAIM_LOG2")) c->claim_cap = atoi(e);
     if (const char *e = getenv("PZ_CTA_WARPS")) c->cta_warps = atoi(e);
     if (const char *e = getenv("PZ_CKPT_EVERY")) c->ckpt_every = atoi(e) == 64 ? 64 : 1024;
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b > 0)
+            c->chunk_bytes = std::min<size_t>(free_b / 2, (size_t)72 << 30);
+    }
     if (const char *e = getenv("PZ_CHUNK_BYTES")) c->chunk_bytes = (size_t)atoll(e);
     *out = c;
     return PZ_OK;

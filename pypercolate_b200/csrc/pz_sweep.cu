@@ -24,6 +24,7 @@
 // Output per bond is one merge record (see pz_common.cuh); per run one word,
 // the first n at which the two spanning sides are joined (hpc.py:269-274).
 #include <cstdio>
+#include <cstdlib>
 #include "pz_common.cuh"
 #include "pz_internal.h"
 
@@ -673,7 +674,13 @@ static SweepPlan plan_team(SweepPlan p, int32_t N, int32_t R, int sms, size_t sm
     int ctas_per_sm = (int)(sm_total / (p.smem_bytes + 1024));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     if (ctas_per_sm > 64 / CTA_WARPS) ctas_per_sm = 64 / CTA_WARPS;
-    if (p.kind == STORE_G32 && ctas_per_sm > 4) ctas_per_sm = 4;
+    {
+        // measured (profiles/sweep_cta_shape_r1.txt): 4-warp CTAs of the global-memory store keep
+        // gaining up to 6 per SM (L = 256: 1.74e10, 3D L = 64: 1.54e10 bonds/s), 8 is no better
+        int cap = 6;                            // PZ_G32_CTAS overrides
+        if (const char *e = getenv("PZ_G32_CTAS")) cap = atoi(e);
+        if (p.kind == STORE_G32 && ctas_per_sm > cap) ctas_per_sm = cap;
+    }
     long long grid = (long long)sms * ctas_per_sm;
     if (grid > R) grid = R;
     if (grid < 1) grid = 1;
