@@ -109,6 +109,8 @@ struct pz_ctx {
     DevBuf<double> pmf;                   // [num_p][M+1], rows in ascending-p order
     DevBuf<int32_t> band_lo, band_hi, tband_lo, tband_hi, porder_dev, canon_flags;
     DevBuf<double> sf;                    // survival functions [num_p][M+1]
+    DevBuf<int32_t> perm_super;           // MT19937 mode: bond orders of a whole super-chunk of runs
+    DevBuf<uint32_t> seed_super;
     DevBuf<double> cols;                  // scratch of the contraction
     DevBuf<double> cols_out;
     const double *canon_last_ptr = nullptr;   // per-run values of the last chunk of the last fused call
@@ -246,6 +248,7 @@ void pz_destroy(pz_ctx *c)
         if (sl.sweep_done) cudaEventDestroy(sl.sweep_done);
         if (sl.stats_done) cudaEventDestroy(sl.stats_done);
     }
+    c->perm_super.release(); c->seed_super.release();
     c->gscratch.release(); c->rows.release(); c->acc.release(); c->span_cum.release();
     c->fin.release(); c->ps_dev.release(); c->band_lo.release();
     c->band_hi.release(); c->tband_lo.release(); c->tband_hi.release(); c->canon_flags.release();
@@ -568,6 +571,34 @@ int pz_run_fused(pz_ctx *c, int32_t R, int perm_mode, const void *perm_src, int 
     if ((flags & PZ_FUSE_CANON) && (c->num_p == 0 || c->pmf_M != c->M || c->sf_M != c->M))
         return fail(PZ_ERR_STATE, "pz_run_fused: PZ_FUSE_CANON needs pz_set_ps(M = bonds of the graph) first");
     PZ_CUDA(cudaSetDevice(c->device));
+    if ((perm_mode & ~PZ_SEEDS_ON_DEVICE) == PZ_PERM_MT19937 && R > 0 && c->M > 0) {
+        // numpy's stream is one serial chain per run (one thread each, a random access per
+        // step): its throughput comes from the number of runs in flight, not from the chunk of
+        // the sweep.  Bond orders are therefore generated for as many runs at once as half the
+        // scratch budget holds, then swept chunk by chunk from device memory.
+        const size_t per = (size_t)c->M * 4;
+        const size_t super = std::max<size_t>(1, std::min<size_t>((size_t)R, (c->chunk_bytes / 2) / per));
+        for (size_t s0 = 0; s0 < (size_t)R; s0 += super) {
+            const int32_t sn = (int32_t)std::min(super, (size_t)R - s0);
+            const uint32_t *seeds_dev = (const uint32_t *)perm_src + s0;
+            if (!(perm_mode & PZ_SEEDS_ON_DEVICE)) {
+                PZ_CUDA(c->seed_super.ensure((size_t)sn));
+                PZ_CUDA(cudaMemcpyAsync(c->seed_super.p, (const uint32_t *)perm_src + s0, (size_t)sn * 4,
+                                        cudaMemcpyHostToDevice, c->stream));
+                seeds_dev = c->seed_super.p;
+            }
+            PZ_CUDA(c->perm_super.ensure((size_t)sn * c->M));
+            int l = 0;
+            {
+                PhaseTimer t(c, PZ_PHASE_PERM);
+                PZ_CUDA(launch_perm_mt19937(c->M, sn, seeds_dev, c->perm_super.p, c->stream, &l));
+            }
+            c->launches += l;
+            rc = pz_run_fused(c, sn, PZ_PERM_DEVICE, c->perm_super.p, flags);
+            if (rc) return rc;
+        }
+        return PZ_OK;
+    }
     if (flags & PZ_FUSE_MICRO) { rc = ensure_acc(c); if (rc) return rc; }
     // everything issued so far on the main stream (graph, weights, resets) must
     // be visible to the side streams
