@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(32 * CTA_WARPS, 1) sweep_cta_kernel(SweepArgs 
         bool track = spanning;                 // CTA-uniform
         uint32_t epoch = 0x003fffffu;          // decreasing: newer claims always win over stale ones
 #ifdef PZ_TIMING
-        long long tm_find = 0, tm_init = clock64(), tm_rounds = 0, tm_t = 0, tm_seg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tm_p = 0, tm_star = 0;
+        long long tm_find = 0, tm_init = clock64(), tm_rounds = 0, tm_t = 0, tm_seg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tm_p = 0, tm_star = 0, tm_late = 0, tm_nlate = 0, tm_b0 = 0; int tm_pc = 0;
 #define TM(k) { const long long _c = clock64(); tm_seg[k] += _c - tm_p; tm_p = _c; }
 #else
 #define TM(k)
@@ -508,7 +508,7 @@ __global__ void __launch_bounds__(32 * CTA_WARPS, 1) sweep_cta_kernel(SweepArgs 
 
             uint32_t ru = 0, rv = 0, tu = 0, tv = 0;
 #ifdef PZ_TIMING
-            tm_t = clock64();
+            tm_t = clock64(); tm_b0 = tm_t;
 #endif
             if (valid) {
                 edge_uv(uv, ru, rv);
@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(32 * CTA_WARPS, 1) sweep_cta_kernel(SweepArgs 
 #ifdef PZ_TIMING
             tm_find += clock64() - tm_t;
             tm_p = clock64();
-            __syncthreads();
+            tm_pc = __syncthreads_count(pending);
             TM(7)
 #endif
             for (;;) {
@@ -630,6 +630,9 @@ __global__ void __launch_bounds__(32 * CTA_WARPS, 1) sweep_cta_kernel(SweepArgs 
                 }
                 TM(7)
             }
+#ifdef PZ_TIMING
+            if (tm_pc < CTA_THREADS / 5) { tm_late += clock64() - tm_b0; ++tm_nlate; }
+#endif
             if (track && sh->span_min != NSPAN_NEVER) track = false;
             if (valid) __stcs(&rec_out[n], rec);
         }
@@ -638,7 +641,8 @@ __global__ void __launch_bounds__(32 * CTA_WARPS, 1) sweep_cta_kernel(SweepArgs 
         if ((tid & 127) == 0 && blockIdx.x == 0 && run < (int)gridDim.x)
             printf("warp %2d: total %lld find %lld (%lld iterations, %lld star) claim %lld bar1 %lld own %lld bar2 %lld merge %lld star %lld bar3 %lld find2+findbar %lld\n",
                    warp, clock64() - tm_init, tm_find, tm_rounds, tm_star,
-                   tm_seg[0], tm_seg[1], tm_seg[2], tm_seg[3], tm_seg[4], tm_seg[5], tm_seg[6], tm_seg[7]);
+                   tm_seg[0], tm_seg[1], tm_seg[2], tm_seg[3], tm_seg[4], tm_seg[5], tm_seg[6], tm_seg[7]),
+            printf("         batches with < T/5 pending bonds: %lld, %lld cycles\n", tm_nlate, tm_late);
 #endif
         if (tid == 0) a.nspan[run] = sh->span_min;
         __syncthreads();
