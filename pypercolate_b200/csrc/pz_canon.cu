@@ -243,10 +243,16 @@ cudaError_t launch_canon_rows(int32_t M, int spanning, const uint8_t *rows, cons
 // non-zero weight) recomputes only flagged chunks, so no term is ever dropped
 // from a result that could notice it.
 // ---------------------------------------------------------------------------
-static constexpr int PC = 8;
+#ifndef PZ_PC
+#define PZ_PC 8
+#endif
+#ifndef PZ_PC_OCC
+#define PZ_PC_OCC 3
+#endif
+static constexpr int PC = PZ_PC;
 
 template <class RecT>
-__global__ void __launch_bounds__(128, 3) canon_runs_kernel(StatsArgs a, int32_t P, int32_t nchunks,
+__global__ void __launch_bounds__(128, PZ_PC_OCC) canon_runs_kernel(StatsArgs a, int32_t P, int32_t nchunks,
                                                              const double *pmf, const double *sf,
                                                              const int32_t *xlo, const int32_t *xhi,
                                                              const int32_t *tlo, const int32_t *thi,

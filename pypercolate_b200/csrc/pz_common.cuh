@@ -54,13 +54,15 @@ struct RunState {
     uint64_t s2, s3, s4;
     __host__ __device__ void init(uint32_t N) { c = 0; mx = 1; s2 = s3 = s4 = N; }
     __host__ __device__ __forceinline__ void merge(uint32_t wa, uint32_t wb) {
-        uint64_t a = wa, b = wb, w = a + b;
-        uint64_t a2 = a * a, b2 = b * b, w2 = w * w;
-        s2 += w2 - a2 - b2;
-        s3 += w2 * w - a2 * a - b2 * b;
-        s4 += w2 * w2 - a2 * a2 - b2 * b2;
+        // with w = a + b and t = a b:  w^2 - a^2 - b^2 = 2t,  w^3 - a^3 - b^3 = 3tw,
+        // w^4 - a^4 - b^4 = 2t (2 w^2 - t)   (identities in Z, hence mod 2^64)
+        const uint32_t w = wa + wb;
+        const uint64_t t = (uint64_t)wa * wb, w2 = (uint64_t)w * w;
+        s2 += 2 * t;
+        s3 += 3 * t * w;
+        s4 += 2 * t * (2 * w2 - t);
         c += 1;
-        if ((uint32_t)w > mx) mx = (uint32_t)w;
+        if (w > mx) mx = w;
     }
     // moments[k], k = 0..4 (hpc.py:214 at n = 0, :283-305 afterwards)
     __host__ __device__ __forceinline__ void moments(uint32_t N, uint64_t m[5]) const {

@@ -36,12 +36,14 @@ template <class RecT>
 __device__ __forceinline__ Delta delta_of(RecT r) {
     Delta d{0, 0, 0, 0, 0};
     if (RecCodec<RecT>::valid(r)) {
-        const uint64_t a = RecCodec<RecT>::w_small(r), b = RecCodec<RecT>::w_large(r), w = a + b;
-        const uint64_t a2 = a * a, b2 = b * b, w2 = w * w;
-        d.c = 1; d.mx = (uint32_t)w;
-        d.s2 = w2 - a2 - b2;
-        d.s3 = w2 * w - a2 * a - b2 * b;
-        d.s4 = w2 * w2 - a2 * a2 - b2 * b2;
+        // w = a + b, t = a b:  w^2 - a^2 - b^2 = 2t,  w^3 - a^3 - b^3 = 3tw,
+        // w^4 - a^4 - b^4 = 2t (2 w^2 - t)   (identities in Z, hence mod 2^64)
+        const uint32_t a = RecCodec<RecT>::w_small(r), b = RecCodec<RecT>::w_large(r), w = a + b;
+        const uint64_t t = (uint64_t)a * b, w2 = (uint64_t)w * w;
+        d.c = 1; d.mx = w;
+        d.s2 = 2 * t;
+        d.s3 = 3 * t * w;
+        d.s4 = 2 * t * (2 * w2 - t);
     }
     return d;
 }
