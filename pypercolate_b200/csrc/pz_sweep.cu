@@ -450,6 +450,7 @@ struct CtaShared {
     unsigned long long scan_tot[CTA_MAX_WARPS];
     uint32_t span_min;
     uint32_t bmin;                            // lowest blocked position of the round
+    uint32_t star_epoch;                      // epoch of the last round in which a star bond was pending
 };
 
 template <class Store, int CTA_WARPS>
@@ -479,6 +480,7 @@ __global__ void __launch_bounds__(32 * CTA_WARPS, 1) sweep_cta_kernel(SweepArgs 
         if (tid == 0) {
             sh->span_min = NSPAN_NEVER;
             sh->bmin = 0xffffffffu;
+            sh->star_epoch = 0xffffffffu;
             sh->hub_key = 1ull << 32;          // node 0, size 1
         }
         __syncthreads();
@@ -542,19 +544,22 @@ __global__ void __launch_bounds__(32 * CTA_WARPS, 1) sweep_cta_kernel(SweepArgs 
                         sv = claim_slot(star ? o : rv, clog);
                         atomicMin(&claim[su], key);
                         if (!star) atomicMin(&claim[sv], key);
+                        else sh->star_epoch = epoch;            // this round needs the star barrier
                     }
                 }
                 TM(0)
                 if (!__syncthreads_or(pending)) break;          // nothing (left) to merge
                 TM(1)
+                const bool star_round = sh->star_epoch == epoch;
                 bool own = false;
                 if (warp_has) {
                     own = pending && claim[su] == key && claim[sv] == key;
-                    if (pending && !own) atomicMin(&sh->bmin, (uint32_t)tid);
+                    if (star_round && pending && !own) atomicMin(&sh->bmin, (uint32_t)tid);
                 }
                 TM(2)
-                const int nstar = __syncthreads_count(own && star);
-                TM(3)
+                // winners that are not star bonds own both roots: they merge right away, no
+                // earlier bond of the batch touches their clusters (star bonds never do either:
+                // those touch the hub and a root they own themselves)
                 bool won = false;
                 if (own && !star) {
                     rec = make_rec<Rec>(Store::size_m1(tu), Store::size_m1(tv));
@@ -566,6 +571,10 @@ __global__ void __launch_bounds__(32 * CTA_WARPS, 1) sweep_cta_kernel(SweepArgs 
                     if (hk > sh->hub_key) atomicMax(&sh->hub_key, hk);
                     won = true;
                 }
+                // rounds without star bonds skip this barrier
+                int nstar = 0;
+                if (star_round) nstar = __syncthreads_count(own && star);
+                TM(3)
                 TM(4)
 #ifdef PZ_TIMING
                 if (nstar) ++tm_star;
