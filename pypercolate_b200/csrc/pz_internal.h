@@ -34,6 +34,7 @@ struct SweepPlan {
     size_t gscratch_bytes;
     int team;                 // 1: finder/merger team kernel (one CTA of 4 warps per run)
     size_t store_bytes;       // team kernel: bytes of the parent store inside the CTA's smem
+    int finders;              // 1: CTA kernel with 8 finder warps next to 16 main warps
 };
 
 // choose store, CTA shape and grid for a graph of N nodes on a device with

@@ -659,6 +659,301 @@ __global__ void __launch_bounds__(32 * CTA_WARPS, 1) sweep_cta_kernel(SweepArgs 
 }
 
 // ---------------------------------------------------------------------------
+// CTA kernel with FINDER warps (the shape used when one run fills the shared memory of an SM).
+// The lock-step rounds leave three quarters of the issue slots idle, and the finds of a batch
+// (a fifth of the lock-step time) depend on nothing but the forest.  So 8 extra warps walk the
+// endpoints of batch b+1 up the forest WHILE the 16 main warps run the rounds of batch b and hand
+// the nodes they reach -- representatives: ancestors-or-self, valid whatever merges happen in
+// between -- to the main warps through a 2 KB buffer.  The main warps start a batch by walking
+// those representatives up to the current roots (0-1 steps) and never execute the find phase.
+//
+// Finders read the forest while merges are in flight.  A node turns from root into child by two
+// stores, parent first, then the root flag with RELEASE order; a finder reads the flag with ACQUIRE
+// order before the value, so a cleared flag always comes with the parent pointer.  The other
+// direction (flag still set, value already a parent) makes the finder stop at a node that was a
+// root a moment ago, which is a valid representative.  Path halving is done by the finders only
+// and touches non-root entries, which merges never write.
+//
+// Named barriers: 1 = the 512 main threads (rounds), 2 = representatives of a batch are in the
+// buffer (finders arrive, mains wait), 3 = the buffer has been read (mains arrive, finders wait).
+// ---------------------------------------------------------------------------
+static constexpr int FW_MAIN_WARPS = 16, FW_FIND_WARPS = 8;
+static constexpr int FW_MAIN = 32 * FW_MAIN_WARPS, FW_FIND = 32 * FW_FIND_WARPS, FW_ALL = FW_MAIN + FW_FIND;
+
+__device__ __forceinline__ void nb_sync(int id, int n) {
+    asm volatile("barrier.cta.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+__device__ __forceinline__ void nb_arrive(int id, int n) {
+    asm volatile("barrier.cta.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+__device__ __forceinline__ bool nb_or(int id, int n, bool pred) {
+    uint32_t r;
+    asm volatile("{\n\t.reg .pred q, o;\n\tsetp.ne.u32 q, %3, 0;\n\tbarrier.cta.red.or.pred o, %1, %2, q;\n\t"
+                 "selp.u32 %0, 1, 0, o;\n\t}"
+                 : "=r"(r) : "r"(id), "r"(n), "r"((uint32_t)pred) : "memory");
+    return r != 0;
+}
+__device__ __forceinline__ int nb_count(int id, int n, bool pred) {
+    uint32_t r;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\tbarrier.cta.red.popc.u32 %0, %1, %2, q;\n\t}"
+                 : "=r"(r) : "r"(id), "r"(n), "r"((uint32_t)pred) : "memory");
+    return (int)r;
+}
+
+// StoreS16B whose root -> child transitions are release stores, plus the finders' acquire walk
+struct StoreS16BF : StoreS16B {
+    __device__ __forceinline__ void clear_flag_release(uint32_t x) {
+        const uint32_t addr = (uint32_t)__cvta_generic_to_shared(flag + x);
+        asm volatile("st.release.cta.shared.u8 [%0], %1;" ::"r"(addr), "r"(0u) : "memory");
+    }
+    __device__ __forceinline__ uint32_t flag_acquire(uint32_t x) const {
+        uint32_t f;
+        const uint32_t addr = (uint32_t)__cvta_generic_to_shared(flag + x);
+        asm volatile("ld.acquire.cta.shared.u8 %0, [%1];" : "=r"(f) : "r"(addr) : "memory");
+        return f;
+    }
+    __device__ __forceinline__ void make_child(uint32_t x, uint32_t parent) {
+        val[x] = (uint16_t)parent;
+        clear_flag_release(x);
+    }
+    __device__ __forceinline__ uint32_t unite(uint32_t ra, uint32_t ta, uint32_t rb, uint32_t tb, bool) {
+        const uint32_t sa = size_m1(ta), sb = size_m1(tb);
+        const uint32_t big = sa >= sb ? ra : rb, small = sa >= sb ? rb : ra;
+        const uint32_t m = ((ta | tb) >> 17) & 3u;
+        val[small] = (uint16_t)big;
+        clear_flag_release(small);
+        val[big] = (uint16_t)(sa + sb + 1);
+        if (m != (((sa >= sb ? ta : tb) >> 17) & 3u)) flag[big] = (uint8_t)(1u | (m << 1));
+        return m;
+    }
+    // finder: walk x up while merges may be in flight; returns an ancestor-or-self of x that
+    // was a root when its flag was read (path halving on the way)
+    __device__ __forceinline__ uint32_t find_rep(uint32_t x) {
+        uint32_t fx = flag_acquire(x);
+        while (!(fx & 1u)) {
+            const uint32_t p = val[x];                  // a parent pointer: the flag was clear
+            const uint32_t fp = flag_acquire(p);
+            if (fp & 1u) { x = p; break; }
+            const uint32_t g = val[p];
+            val[x] = (uint16_t)g;                       // halve: parent[x] = grandparent
+            x = g;
+            fx = flag_acquire(x);
+        }
+        return x;
+    }
+};
+
+template <class Store>
+__global__ void __launch_bounds__(FW_ALL, 1) sweep_fw_kernel(SweepArgs a, uint32_t store_bytes)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    using Rec = typename Store::Rec;
+    using Edge = typename Store::Edge;
+    constexpr int CTA_WARPS = FW_MAIN_WARPS;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool finder = tid >= FW_MAIN;
+    const int M = a.M;
+    const int clog = a.claim_log2;
+
+    uint32_t *claim = reinterpret_cast<uint32_t *>(smem);
+    unsigned char *p = smem + (sizeof(uint32_t) << clog);
+    Store st;
+    st.bind(p, a, blockIdx.x);
+    CtaShared *sh = reinterpret_cast<CtaShared *>(p + store_bytes);
+    uint32_t *reps = reinterpret_cast<uint32_t *>(p + store_bytes + 320);      // [FW_MAIN] ru | rv << 16
+
+    const Edge *edges = reinterpret_cast<const Edge *>(a.edges);
+    const bool spanning = a.sides2 != nullptr;
+    const int nb = (M + FW_MAIN - 1) / FW_MAIN;
+
+    for (int run = blockIdx.x; run < a.R; run += gridDim.x) {
+        st.init(tid, FW_ALL);
+        for (int i = tid; i < (1 << clog); i += FW_ALL) claim[i] = CLAIM_FREE;
+        if (tid == 0) {
+            sh->span_min = NSPAN_NEVER;
+            sh->bmin = 0xffffffffu;
+            sh->star_epoch = 0xffffffffu;
+            sh->hub_key = 1ull << 32;          // node 0, size 1
+        }
+        __syncthreads();
+        const int32_t *perm = a.perms + (size_t)run * M;
+
+        if (finder) {
+            // ---- finder warps: two bonds per thread and batch ------------------------------
+            const int ft = tid - FW_MAIN;
+            Edge uv_next[2] = {Edge(), Edge()};
+            int32_t e_next[2] = {0, 0};
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int n = ft + q * FW_FIND;
+                if (n < M) uv_next[q] = __ldg(&edges[__ldcs(&perm[n])]);
+                if (n + FW_MAIN < M) e_next[q] = __ldcs(&perm[n + FW_MAIN]);
+            }
+            for (int b = 0; b < nb; ++b) {
+                uint32_t out[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int n = b * FW_MAIN + ft + q * FW_FIND;
+                    const Edge uv = uv_next[q];
+                    if (n + FW_MAIN < M) uv_next[q] = __ldg(&edges[e_next[q]]);
+                    if (n + 2 * FW_MAIN < M) e_next[q] = __ldcs(&perm[n + 2 * FW_MAIN]);
+                    uint32_t u = 0, v = 0;
+                    if (n < M) {
+                        edge_uv(uv, u, v);
+                        u = st.find_rep(u);
+                        v = st.find_rep(v);
+                    }
+                    out[q] = u | (v << 16);
+                }
+                nb_sync(3, FW_ALL);                     // the buffer of the previous batch has been read
+                reps[ft] = out[0];
+                reps[ft + FW_FIND] = out[1];
+                nb_arrive(2, FW_ALL);                   // representatives of batch b are in the buffer
+            }
+        } else {
+            // ---- main warps: rounds -----------------------------------------------------------
+            Rec *rec_out = reinterpret_cast<Rec *>(a.recs) + (size_t)run * M;
+            bool track = spanning;                 // uniform over the main warps
+            uint32_t epoch = 0x003fffffu;          // decreasing: newer claims always win over stale ones
+            nb_arrive(3, FW_ALL);                  // the buffer is free
+#ifdef PZ_TIMING
+            long long fw_wait = 0, fw_walk = 0;
+            const long long fw_t0 = clock64();
+#endif
+            for (int b = 0; b < nb; ++b) {
+                const int n = b * FW_MAIN + tid;   // bond index; row index is n + 1
+                const bool valid = n < M;
+#ifdef PZ_TIMING
+                const long long tw0 = clock64();
+#endif
+                nb_sync(2, FW_ALL);
+#ifdef PZ_TIMING
+                const long long tw1 = clock64();
+                fw_wait += tw1 - tw0;
+#endif
+                const uint32_t rep = reps[tid];
+                if (b + 1 < nb) nb_arrive(3, FW_ALL);
+                uint32_t ru = rep & 0xffffu, rv = rep >> 16, tu = 0, tv = 0;
+                if (valid) st.find2(ru, rv, tu, tv);        // up to the current roots
+#ifdef PZ_TIMING
+                fw_walk += clock64() - tw1;
+#endif
+                bool pending = valid && ru != rv;
+                Rec rec = 0;
+                for (;;) {
+                    // a warp without pending bonds only takes part in the barriers
+                    const bool warp_has = __any_sync(0xffffffffu, pending);
+                    const uint32_t key = (epoch << 10) | (uint32_t)tid;
+                    uint32_t hub = 0, o = 0, to = 0, th = 0, su = 0, sv = 0;
+                    bool star = false;
+                    if (warp_has) {
+                        hub = (uint32_t)sh->hub_key;
+                        // star bond: one side is the hub; o = the other root
+                        star = pending && (ru == hub || rv == hub);
+                        o = ru == hub ? rv : ru; to = ru == hub ? tv : tu;
+                        th = ru == hub ? tu : tv;
+                        if (pending) {
+                            su = claim_slot(star ? o : ru, clog);
+                            sv = claim_slot(star ? o : rv, clog);
+                            atomicMin(&claim[su], key);
+                            if (!star) atomicMin(&claim[sv], key);
+                            else sh->star_epoch = epoch;            // this round needs the star barrier
+                        }
+                    }
+                    if (!nb_or(1, FW_MAIN, pending)) break;         // nothing (left) to merge
+                    const bool star_round = sh->star_epoch == epoch;
+                    bool own = false;
+                    if (warp_has) {
+                        own = pending && claim[su] == key && claim[sv] == key;
+                        if (star_round && pending && !own) atomicMin(&sh->bmin, (uint32_t)tid);
+                    }
+                    bool won = false;
+                    if (own && !star) {
+                        rec = make_rec<Rec>(Store::size_m1(tu), Store::size_m1(tv));
+                        const uint32_t sz = Store::size_m1(tu) + Store::size_m1(tv) + 2;
+                        const uint32_t m = st.unite(ru, tu, rv, tv, track);
+                        if (track && (m == 3u || a.any3)) atomicMin(&sh->span_min, (uint32_t)n + 1);
+                        const uint32_t big = Store::size_m1(tu) >= Store::size_m1(tv) ? ru : rv;
+                        const unsigned long long hk = ((unsigned long long)sz << 32) | big;
+                        if (hk > sh->hub_key) atomicMax(&sh->hub_key, hk);
+                        won = true;
+                    }
+                    int nstar = 0;
+                    if (star_round) nstar = nb_count(1, FW_MAIN, own && star);
+                    if (nstar) {
+                        // star bonds merge together iff no earlier bond of the batch is blocked
+                        const bool sw = own && star && (uint32_t)tid < sh->bmin;
+                        unsigned long long v = 0ull, incl = 0ull;
+                        if (__any_sync(0xffffffffu, sw)) {
+                            const uint32_t so = sw ? st.sides_of_root(o, to) : 0u;
+                            v = sw ? ((unsigned long long)(Store::size_m1(to) + 1) |
+                                      ((unsigned long long)(so & 1u) << 40) |
+                                      ((unsigned long long)(so >> 1) << 50)) : 0ull;
+                            incl = v;
+#pragma unroll
+                            for (int k = 1; k < 32; k <<= 1) {
+                                const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, k);
+                                if (lane >= k) incl += t;
+                            }
+                        }
+                        if (lane == 31) sh->scan_tot[warp] = incl;
+                        nb_sync(1, FW_MAIN);
+                        if (sw) {
+                            unsigned long long pre = incl - v, total = 0;
+#pragma unroll
+                            for (int w = 0; w < CTA_WARPS; ++w) {
+                                const unsigned long long t = sh->scan_tot[w];
+                                if (w < warp) pre += t;
+                                total += t;
+                            }
+                            const uint32_t hub_m1 = Store::size_m1(th);     // hub size - 1 at round start
+                            const uint32_t pre_sz = (uint32_t)(pre & 0xffffffffffull);
+                            rec = make_rec<Rec>(Store::size_m1(to), hub_m1 + pre_sz);
+                            st.make_child(o, hub);
+                            if (track) {
+                                const uint32_t hs = st.sides_of_root(hub, th);
+                                const unsigned long long in = pre + v;
+                                const uint32_t m = hs | (((in >> 40) & 0x3ffu) ? 1u : 0u) |
+                                                   (((in >> 50) & 0x3ffu) ? 2u : 0u);
+                                if (m == 3u || a.any3) atomicMin(&sh->span_min, (uint32_t)n + 1);
+                            }
+                            if (pre_sz == 0) {      // first star bond of the round: publish the hub
+                                const uint32_t tot_sz = (uint32_t)(total & 0xffffffffffull);
+                                const uint32_t add = (((total >> 40) & 0x3ffu) ? 1u : 0u) |
+                                                     (((total >> 50) & 0x3ffu) ? 2u : 0u);
+                                st.set_root(hub, hub_m1 + tot_sz, track ? add : 0u);
+                                atomicMax(&sh->hub_key,
+                                          ((unsigned long long)(hub_m1 + tot_sz + 1) << 32) | hub);
+                            }
+                            won = true;
+                        }
+                    }
+                    if (won) pending = false;
+                    --epoch;
+                    if (tid == 0) sh->bmin = 0xffffffffu;
+                    if (!nb_or(1, FW_MAIN, pending)) break;         // every candidate merged
+                    if (pending) {                                  // walk up to the new roots
+                        st.find2(ru, rv, tu, tv);
+                        pending = ru != rv;
+                    }
+                }
+                if (track && sh->span_min != NSPAN_NEVER) track = false;
+                if (valid) __stcs(&rec_out[n], rec);
+            }
+#ifdef PZ_TIMING
+            if ((tid & 127) == 0 && blockIdx.x == 0 && run < (int)gridDim.x)
+                printf("fw warp %2d: total %lld, waiting for representatives %lld, walking them up %lld\n",
+                       warp, clock64() - fw_t0, fw_wait, fw_walk);
+#endif
+        }
+        __syncthreads();
+        if (tid == 0) a.nspan[run] = sh->span_min;
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
 // planning and launch
 // ---------------------------------------------------------------------------
 
@@ -683,6 +978,17 @@ static SweepPlan plan_team(SweepPlan p, int32_t N, int32_t R, int sms, size_t sm
     p.store_bytes = store_bytes;
     p.warps_per_cta = CTA_WARPS;
     p.smem_bytes = align16h(fixed + ((size_t)4 << clog));
+    // one run per SM (shared-memory store, 16 warps): finder warps walk the next batch up the forest
+    // while the main warps run the rounds (PZ_FINDERS=0 switches them off)
+    p.finders = 0;
+    if (p.kind == STORE_S16B && CTA_WARPS == 16) {
+        int want = 1;
+        if (const char *e = getenv("PZ_FINDERS")) want = atoi(e);
+        if (want && align16h(fixed + ((size_t)4 << clog) + 4 * FW_MAIN) <= smem_optin) {
+            p.finders = 1;
+            p.smem_bytes = align16h(fixed + ((size_t)4 << clog) + 4 * FW_MAIN);
+        }
+    }
     p.slice_bytes = p.smem_bytes;
     int ctas_per_sm = (int)(sm_total / (p.smem_bytes + 1024));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
@@ -806,6 +1112,13 @@ static cudaError_t launch_t(const SweepPlan &p, const SweepArgs &a, cudaStream_t
 
 cudaError_t launch_sweep(const SweepPlan &p, const SweepArgs &a, cudaStream_t s)
 {
+    if (p.team && p.finders) {
+        cudaError_t e = cudaFuncSetAttribute(sweep_fw_kernel<StoreS16BF>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
+        if (e != cudaSuccess) return e;
+        sweep_fw_kernel<StoreS16BF><<<p.grid, FW_ALL, p.smem_bytes, s>>>(a, (uint32_t)p.store_bytes);
+        return cudaGetLastError();
+    }
     if (p.team) {
         switch (p.kind) {
         case STORE_S16: return launch_team_t<StoreS16>(p, a, s);

@@ -552,6 +552,45 @@ def test_statistical_agreement_of_philox_mode(mode_name):
         assert abs(m0 - m1) < 5 * s
 
 
+@pytest.mark.parametrize("L,runs", [(256, 3000), (200, 2000), (182, 1500)])
+def test_finder_warps_match_lock_step_kernel(L, runs):
+    """One run per SM (32768 < N <= 65536): 8 finder warps walk the next batch up the forest while
+    merges are in flight (release/acquire on the root flags).  Thousands of full runs must give
+    exactly the sums and canonical partials of the plain lock-step kernel, and the first runs
+    the oracle's rows."""
+    from pypercolate_b200 import lowering
+    from oracle import oracle
+    n = _native()
+    g = lowering.lowered_spanning_2d_grid(L)
+    N, M = g.num_nodes, g.num_edges
+    seeds = np.arange(runs, dtype=np.uint32) * 7919 + 13
+    ps = np.linspace(0.45, 0.55, 7)
+    got = {}
+    for finders in ("0", "1"):
+        old = os.environ.get("PZ_FINDERS")
+        os.environ["PZ_FINDERS"] = finders
+        try:
+            ctx = n.Context(0)
+        finally:
+            if old is None:
+                os.environ.pop("PZ_FINDERS", None)
+            else:
+                os.environ["PZ_FINDERS"] = old
+        ctx.set_graph(g)
+        ctx.set_ps(ps)
+        ctx.run_fused(runs, n.PERM_FEISTEL, seeds, n.FUSE_MICRO | n.FUSE_CANON)
+        got[finders] = (ctx.micro_export(), ctx.canon_export())
+        if finders == "1":
+            rows, perms = ctx.run_rows(3, n.PERM_FEISTEL, seeds[:3], want_perms=True)
+            for r in range(3):
+                ref = oracle.sweep_rows(N, M, g.eu, g.ev, g.side_mask, False, perms[r])
+                assert_rows_equal(rows[r], ref, "finder warps L=%d" % L)
+        ctx.close()
+    assert np.array_equal(acc_totals(got["0"][0]), acc_totals(got["1"][0]))
+    assert got["0"][1][0] == got["1"][1][0]
+    assert np.array_equal(got["0"][1][1], got["1"][1][1]) and np.array_equal(got["0"][1][2], got["1"][1][2])
+
+
 def test_missing_graph_and_bad_arguments_fail_loudly():
     n = _native()
     ctx = n.Context(0)
@@ -574,6 +613,7 @@ def test_missing_graph_and_bad_arguments_fail_loudly():
 @pytest.mark.parametrize("env", [{"PZ_PIPELINE": "1"}, {"PZ_PIPELINE": "2"}, {"PZ_SWEEP_TEAM": "0"},
                                  {"PZ_CTA_WARPS": "2"}, {"PZ_CTA_WARPS": "32"},
                                  {"PZ_CTA_WARPS": "8", "PZ_CLAIM_LOG2": "8"}, {"PZ_CHUNK_BYTES": "3000000"},
+                                 {"PZ_FINDERS": "0"},
                                  {"PZ_CKPT_EVERY": "1024"}])
 def test_alternative_launch_shapes_give_identical_results(env):
     """Three-stream pipelining, the single-warp A/B kernel, other CTA shapes, a tiny (collision
