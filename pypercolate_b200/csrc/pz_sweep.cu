@@ -677,8 +677,12 @@ __global__ void __launch_bounds__(32 * CTA_WARPS, 1) sweep_cta_kernel(SweepArgs 
 // Named barriers: 1 = the 512 main threads (rounds), 2 = representatives of a batch are in the
 // buffer (finders arrive, mains wait), 3 = the buffer has been read (mains arrive, finders wait).
 // ---------------------------------------------------------------------------
-static constexpr int FW_MAIN_WARPS = 16, FW_FIND_WARPS = 8;
+#ifndef PZ_FW_WARPS
+#define PZ_FW_WARPS 8
+#endif
+static constexpr int FW_MAIN_WARPS = 16, FW_FIND_WARPS = PZ_FW_WARPS;
 static constexpr int FW_MAIN = 32 * FW_MAIN_WARPS, FW_FIND = 32 * FW_FIND_WARPS, FW_ALL = FW_MAIN + FW_FIND;
+static constexpr int FW_BPT = FW_MAIN / FW_FIND;          // bonds per finder thread and batch
 
 __device__ __forceinline__ void nb_sync(int id, int n) {
     asm volatile("barrier.cta.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
@@ -780,20 +784,21 @@ __global__ void __launch_bounds__(FW_ALL, 1) sweep_fw_kernel(SweepArgs a, uint32
         const int32_t *perm = a.perms + (size_t)run * M;
 
         if (finder) {
-            // ---- finder warps: two bonds per thread and batch ------------------------------
+            // ---- finder warps: FW_BPT bonds per thread and batch -----------------------------
             const int ft = tid - FW_MAIN;
-            Edge uv_next[2] = {Edge(), Edge()};
-            int32_t e_next[2] = {0, 0};
+            Edge uv_next[FW_BPT];
+            int32_t e_next[FW_BPT];
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
+            for (int q = 0; q < FW_BPT; ++q) {
+                uv_next[q] = Edge(); e_next[q] = 0;
                 const int n = ft + q * FW_FIND;
                 if (n < M) uv_next[q] = __ldg(&edges[__ldcs(&perm[n])]);
                 if (n + FW_MAIN < M) e_next[q] = __ldcs(&perm[n + FW_MAIN]);
             }
             for (int b = 0; b < nb; ++b) {
-                uint32_t out[2];
+                uint32_t out[FW_BPT];
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
+                for (int q = 0; q < FW_BPT; ++q) {
                     const int n = b * FW_MAIN + ft + q * FW_FIND;
                     const Edge uv = uv_next[q];
                     if (n + FW_MAIN < M) uv_next[q] = __ldg(&edges[e_next[q]]);
@@ -807,8 +812,8 @@ __global__ void __launch_bounds__(FW_ALL, 1) sweep_fw_kernel(SweepArgs a, uint32
                     out[q] = u | (v << 16);
                 }
                 nb_sync(3, FW_ALL);                     // the buffer of the previous batch has been read
-                reps[ft] = out[0];
-                reps[ft + FW_FIND] = out[1];
+#pragma unroll
+                for (int q = 0; q < FW_BPT; ++q) reps[ft + q * FW_FIND] = out[q];
                 nb_arrive(2, FW_ALL);                   // representatives of batch b are in the buffer
             }
         } else {
@@ -816,7 +821,7 @@ __global__ void __launch_bounds__(FW_ALL, 1) sweep_fw_kernel(SweepArgs a, uint32
             Rec *rec_out = reinterpret_cast<Rec *>(a.recs) + (size_t)run * M;
             bool track = spanning;                 // uniform over the main warps
             uint32_t epoch = 0x003fffffu;          // decreasing: newer claims always win over stale ones
-            nb_arrive(3, FW_ALL);                  // the buffer is free
+            if (nb > 0) nb_arrive(3, FW_ALL);      // the buffer is free
 #ifdef PZ_TIMING
             long long fw_wait = 0, fw_walk = 0;
             const long long fw_t0 = clock64();

@@ -591,6 +591,39 @@ def test_finder_warps_match_lock_step_kernel(L, runs):
     assert np.array_equal(got["0"][1][1], got["1"][1][1]) and np.array_equal(got["0"][1][2], got["1"][1][2])
 
 
+def test_finder_warps_on_sparse_and_empty_graphs():
+    """The one-run-per-SM shape (32768 < N <= 65536) on graphs that are not lattices: no bonds at
+    all, fewer bonds than one batch, a long chain, a random sparse graph."""
+    from pypercolate_b200 import lowering
+    from oracle import oracle
+    n = _native()
+    N = 40000
+    rng = np.random.RandomState(5)
+    cases = [
+        ([], []),
+        (list(range(0, 300)), list(range(1, 301))),
+        (list(range(0, N - 1)), list(range(1, N))),
+        (rng.randint(0, N, size=60000).tolist(), rng.randint(0, N, size=60000).tolist()),
+    ]
+    side = np.zeros(N, dtype=np.uint8)
+    side[:50] = 1
+    side[-50:] = 2
+    for eu, ev in cases:
+        keep = [(a, b) for a, b in zip(eu, ev) if a != b]
+        eu, ev = [a for a, _ in keep], [b for _, b in keep]
+        g = lowering.LoweredGraph(N, eu, ev, side_mask=side)
+        ctx = ctx_for(g)
+        M = g.num_edges
+        runs = 5
+        perms = np.stack([oracle.numpy_permutation(90 + r, M) for r in range(runs)]) if M else \
+            np.zeros((runs, 0), np.int32)
+        rows = ctx.run_rows(runs, n.PERM_HOST, perms)
+        for r in range(runs):
+            ref = oracle.sweep_rows(N, M, g.eu, g.ev, g.side_mask, g.preconnected, perms[r])
+            assert_rows_equal(rows[r], ref, "sparse graph M=%d" % M)
+        ctx.close()
+
+
 def test_missing_graph_and_bad_arguments_fail_loudly():
     n = _native()
     ctx = n.Context(0)
