@@ -678,7 +678,7 @@ __global__ void __launch_bounds__(32 * CTA_WARPS, 1) sweep_cta_kernel(SweepArgs 
 // buffer (finders arrive, mains wait), 3 = the buffer has been read (mains arrive, finders wait).
 // ---------------------------------------------------------------------------
 #ifndef PZ_FW_WARPS
-#define PZ_FW_WARPS 8
+#define PZ_FW_WARPS 4
 #endif
 static constexpr int FW_MAIN_WARPS = 16, FW_FIND_WARPS = PZ_FW_WARPS;
 static constexpr int FW_MAIN = 32 * FW_MAIN_WARPS, FW_FIND = 32 * FW_FIND_WARPS, FW_ALL = FW_MAIN + FW_FIND;
@@ -747,8 +747,10 @@ struct StoreS16BF : StoreS16B {
     }
 };
 
+// (launch bound = the CTA plus one 256-thread CTA of the bond-order kernel: that caps the registers
+// at 72 per thread, so that perm_feistel_kernel of the next chunk still finds room on the SM)
 template <class Store>
-__global__ void __launch_bounds__(FW_ALL, 1) sweep_fw_kernel(SweepArgs a, uint32_t store_bytes)
+__global__ void __launch_bounds__(FW_ALL + 256, 1) sweep_fw_kernel(SweepArgs a, uint32_t store_bytes)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     using Rec = typename Store::Rec;
@@ -760,12 +762,16 @@ __global__ void __launch_bounds__(FW_ALL, 1) sweep_fw_kernel(SweepArgs a, uint32
     const int M = a.M;
     const int clog = a.claim_log2;
 
+    // the last FW_MAIN words of the claim table's 2^clog are the hand-over buffer (a slot index
+    // beyond the shortened table is folded back), so the kernel needs no more shared memory than
+    // the plain one and the bond-order kernel of the next chunk still fits next to it
     uint32_t *claim = reinterpret_cast<uint32_t *>(smem);
+    const uint32_t claim_n = (1u << clog) - FW_MAIN;
+    uint32_t *reps = claim + claim_n;                                          // [FW_MAIN] ru | rv << 16
     unsigned char *p = smem + (sizeof(uint32_t) << clog);
     Store st;
     st.bind(p, a, blockIdx.x);
     CtaShared *sh = reinterpret_cast<CtaShared *>(p + store_bytes);
-    uint32_t *reps = reinterpret_cast<uint32_t *>(p + store_bytes + 320);      // [FW_MAIN] ru | rv << 16
 
     const Edge *edges = reinterpret_cast<const Edge *>(a.edges);
     const bool spanning = a.sides2 != nullptr;
@@ -773,7 +779,7 @@ __global__ void __launch_bounds__(FW_ALL, 1) sweep_fw_kernel(SweepArgs a, uint32
 
     for (int run = blockIdx.x; run < a.R; run += gridDim.x) {
         st.init(tid, FW_ALL);
-        for (int i = tid; i < (1 << clog); i += FW_ALL) claim[i] = CLAIM_FREE;
+        for (int i = tid; i < (int)claim_n; i += FW_ALL) claim[i] = CLAIM_FREE;
         if (tid == 0) {
             sh->span_min = NSPAN_NEVER;
             sh->bmin = 0xffffffffu;
@@ -861,6 +867,8 @@ __global__ void __launch_bounds__(FW_ALL, 1) sweep_fw_kernel(SweepArgs a, uint32
                         if (pending) {
                             su = claim_slot(star ? o : ru, clog);
                             sv = claim_slot(star ? o : rv, clog);
+                            if (su >= claim_n) su -= claim_n;
+                            if (sv >= claim_n) sv -= claim_n;
                             atomicMin(&claim[su], key);
                             if (!star) atomicMin(&claim[sv], key);
                             else sh->star_epoch = epoch;            // this round needs the star barrier
@@ -989,10 +997,7 @@ static SweepPlan plan_team(SweepPlan p, int32_t N, int32_t R, int sms, size_t sm
     if (p.kind == STORE_S16B && CTA_WARPS == 16) {
         int want = 1;
         if (const char *e = getenv("PZ_FINDERS")) want = atoi(e);
-        if (want && align16h(fixed + ((size_t)4 << clog) + 4 * FW_MAIN) <= smem_optin) {
-            p.finders = 1;
-            p.smem_bytes = align16h(fixed + ((size_t)4 << clog) + 4 * FW_MAIN);
-        }
+        if (want && clog >= 11) p.finders = 1;      // (the hand-over buffer is carved out of the claim table)
     }
     p.slice_bytes = p.smem_bytes;
     int ctas_per_sm = (int)(sm_total / (p.smem_bytes + 1024));
