@@ -299,7 +299,7 @@ def main():
             "config": workload_config(world, args.runs, args.rng),
             "runs_per_s": float(args.runs) * args.steps / (ms * 1e-3),
             "roofline": {
-                "bound": "hbm", "kernel": "sweep_cta_kernel (union-find; shared-memory latency bound, see DESIGN.md)",
+                "bound": "hbm", "kernel": "sweep_fw_kernel (union-find sweep, 16 main + 4 finder warps per run; shared-memory latency bound, see DESIGN.md)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_bond": ALGO_BYTES_PER_BOND,
