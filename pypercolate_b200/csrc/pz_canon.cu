@@ -243,16 +243,12 @@ cudaError_t launch_canon_rows(int32_t M, int spanning, const uint8_t *rows, cons
 // non-zero weight) recomputes only flagged chunks, so no term is ever dropped
 // from a result that could notice it.
 // ---------------------------------------------------------------------------
-#ifndef PZ_PC
-#define PZ_PC 8
-#endif
-#ifndef PZ_PC_OCC
-#define PZ_PC_OCC 3
-#endif
-static constexpr int PC = PZ_PC;
+// probabilities per warp: 8 (48 fp64 accumulators) when the batch has enough runs to fill the
+// GPU, 4 for short batches of large graphs (twice the warps; c4: 1e3 runs of L = 1024)
 
-template <class RecT>
-__global__ void __launch_bounds__(128, PZ_PC_OCC) canon_runs_kernel(StatsArgs a, int32_t P, int32_t nchunks,
+
+template <class RecT, int PC>
+__global__ void __launch_bounds__(128, 3) canon_runs_kernel(StatsArgs a, int32_t P, int32_t nchunks,
                                                              const double *pmf, const double *sf,
                                                              const int32_t *xlo, const int32_t *xhi,
                                                              const int32_t *tlo, const int32_t *thi,
@@ -385,20 +381,26 @@ cudaError_t launch_canon_runs(const StatsArgs &a, int32_t P, const double *pmf, 
                               int ckpt_every, int n_ckpt, double *out, int *flags, cudaStream_t s)
 {
     if (a.R <= 0 || P <= 0) return cudaSuccess;
-    const int nchunks = (P + PC - 1) / PC;
-    const long long warps = (long long)((a.R + 31) / 32) * nchunks;
+    int sms = 148;
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const long long groups = (a.R + 31) / 32;
+    const bool narrow = groups * ((P + 7) / 8) < (long long)sms * 12;      // cannot fill 12 warps per SM
+    const int pc = narrow ? 4 : 8;
+    const int nchunks = (P + pc - 1) / pc;
+    const long long warps = groups * nchunks;
     const int grid = (int)((warps + 3) / 4);
     cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(int) * nchunks, s);
     if (e != cudaSuccess) return e;
     for (int pass = 0; pass < 2; ++pass) {
-        if (a.rec64)
-            canon_runs_kernel<uint64_t><<<grid, 128, 0, s>>>(a, P, nchunks, pmf, sf, xlo, xhi, tlo, thi,
-                                                              porder, ckpt, ckpt_every, n_ckpt, out,
-                                                              flags, pass);
-        else
-            canon_runs_kernel<uint32_t><<<grid, 128, 0, s>>>(a, P, nchunks, pmf, sf, xlo, xhi, tlo, thi,
-                                                              porder, ckpt, ckpt_every, n_ckpt, out,
-                                                              flags, pass);
+#define PZ_CANON_LAUNCH(T, C)                                                                          \
+        canon_runs_kernel<T, C><<<grid, 128, 0, s>>>(a, P, nchunks, pmf, sf, xlo, xhi, tlo, thi, porder, \
+                                                     ckpt, ckpt_every, n_ckpt, out, flags, pass)
+        if (a.rec64) { if (narrow) PZ_CANON_LAUNCH(uint64_t, 4); else PZ_CANON_LAUNCH(uint64_t, 8); }
+        else { if (narrow) PZ_CANON_LAUNCH(uint32_t, 4); else PZ_CANON_LAUNCH(uint32_t, 8); }
+#undef PZ_CANON_LAUNCH
     }
     return cudaGetLastError();
 }

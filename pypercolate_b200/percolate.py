@@ -320,6 +320,36 @@ def _microcanonical_average_moments(moments, alpha):
     return ret
 
 
+# credible intervals already evaluated, per (runs, alpha): [known[k], lo[k], hi[k]] for k = 0..runs
+_BETA_TABLES = {}
+_BETA_TABLES_MAX = 4
+
+
+def _beta_interval_rows(k, runs, alpha):
+    """``beta.ppf([alpha/2, 1 - alpha/2], k + 1, runs - k + 1)`` for every entry of the integer-valued
+    array ``k`` (percolate/percolate.py:561-570), shape ``k.shape + (2,)``.
+
+    The interval is a pure function of ``(k, runs, alpha)``: it is evaluated once per distinct k and
+    kept in a table per ``(runs, alpha)``, so that repeated studies with the same number of runs
+    (where the same counts come up again and again) do not pay scipy's root finder twice."""
+    runs = int(runs)
+    key = (runs, float(alpha))
+    tab = _BETA_TABLES.get(key)
+    if tab is None:
+        if len(_BETA_TABLES) >= _BETA_TABLES_MAX:
+            _BETA_TABLES.pop(next(iter(_BETA_TABLES)))
+        tab = [np.zeros(runs + 1, dtype=bool), np.empty(runs + 1), np.empty(runs + 1)]
+        _BETA_TABLES[key] = tab
+    known, lo, hi = tab
+    ki = np.asarray(k).astype(np.int64)
+    need = np.unique(ki[~known[ki]])
+    if need.size:
+        q = scipy.stats.beta.ppf([[alpha / 2], [1 - alpha / 2]], need + 1.0, runs - need + 1.0)
+        lo[need], hi[need] = q[0], q[1]
+        known[need] = True
+    return np.stack([lo[ki], hi[ki]], axis=-1)
+
+
 def _interval(mean, var, runs, alpha):
     """Student-t interval per n from device means / exact variances
     (percolate/percolate.py:613-635, 681-705 vectorised over n).
@@ -467,10 +497,7 @@ def _arrays_from_device(mean, var, runs, alpha, num_nodes, num_edges, spanning):
         # (k + 1) / (runs + 2) and the beta credible interval, evaluated once
         # per distinct k (percolate/percolate.py:561-570)
         ret['spanning_cluster'] = (k + 1) / (runs + 2)
-        ks, inv = np.unique(k, return_inverse=True)
-        table = scipy.stats.beta.ppf(
-            [[alpha / 2], [1 - alpha / 2]], ks + 1, runs - ks + 1).T
-        ret['spanning_cluster_ci'] = table[inv]
+        ret['spanning_cluster_ci'] = _beta_interval_rows(k, runs, alpha)
     ret['M'] = num_edges
     ret['N'] = num_nodes
     return ret
