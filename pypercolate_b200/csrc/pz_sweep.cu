@@ -749,6 +749,15 @@ struct StoreS16BF : StoreS16B {
 
 // (launch bound = the CTA plus one 256-thread CTA of the bond-order kernel: that caps the registers
 // at 72 per thread, so that perm_feistel_kernel of the next chunk still finds room on the SM)
+// hand-over area of the tail mode (see below): at most 32 pending bonds of a batch, in batch order
+struct TailShared {
+    uint32_t wcnt[FW_MAIN_WARPS];             // pending bonds per main warp
+    uint32_t iu[32], iv[32], in[32];          // representatives and bond index of item k
+    unsigned long long irec[32];              // its merge record (0 = joined nothing)
+    uint32_t epoch;                           // epoch after the tail rounds
+};
+static_assert(sizeof(TailShared) <= 768, "TailShared must fit the planner's reserve");
+
 template <class Store>
 __global__ void __launch_bounds__(FW_ALL + 256, 1) sweep_fw_kernel(SweepArgs a, uint32_t store_bytes)
 {
@@ -772,6 +781,7 @@ __global__ void __launch_bounds__(FW_ALL + 256, 1) sweep_fw_kernel(SweepArgs a, 
     Store st;
     st.bind(p, a, blockIdx.x);
     CtaShared *sh = reinterpret_cast<CtaShared *>(p + store_bytes);
+    TailShared *ts = reinterpret_cast<TailShared *>(p + store_bytes + 320);
 
     const Edge *edges = reinterpret_cast<const Edge *>(a.edges);
     const bool spanning = a.sides2 != nullptr;
@@ -829,7 +839,7 @@ __global__ void __launch_bounds__(FW_ALL + 256, 1) sweep_fw_kernel(SweepArgs a, 
             uint32_t epoch = 0x003fffffu;          // decreasing: newer claims always win over stale ones
             if (nb > 0) nb_arrive(3, FW_ALL);      // the buffer is free
 #ifdef PZ_TIMING
-            long long fw_wait = 0, fw_walk = 0;
+            long long fw_wait = 0, fw_walk = 0, fw_tail = 0, fw_ntail = 0, fw_trounds = 0, fw_cta = 0, fw_ncta = 0, fw_titems = 0;
             const long long fw_t0 = clock64();
 #endif
             for (int b = 0; b < nb; ++b) {
@@ -852,8 +862,133 @@ __global__ void __launch_bounds__(FW_ALL + 256, 1) sweep_fw_kernel(SweepArgs a, 
 #endif
                 bool pending = valid && ru != rv;
                 Rec rec = 0;
-                for (;;) {
-                    // a warp without pending bonds only takes part in the barriers
+                for (bool first = true;; first = false) {
+                    // how many bonds of the batch are still pending (the barrier also puts the merges
+                    // of the previous round in front of the walks below)
+                    const int left = nb_count(1, FW_MAIN, pending);
+                    if (left == 0) break;
+#ifdef PZ_TIMING
+                    const long long fw_r0 = clock64();
+#endif
+                    if (left <= 32) {
+#ifdef PZ_TIMING
+                        ++fw_ntail; fw_titems += left;
+#endif
+                        // ---- tail mode.  Half of all rounds start with at most 32 pending bonds
+                        // (late batches, the losers of a conflict, chains through a large cluster),
+                        // and a CTA round costs three barriers over 16 warps whatever the number of
+                        // bonds.  The pending bonds are packed, in batch order, into warp 0, which
+                        // finishes the batch with warp-level rounds (same rules: claims, owners merge,
+                        // star bonds below the first blocked bond merge together) while the others wait.
+                        const uint32_t bal = __ballot_sync(0xffffffffu, pending);
+                        if (lane == 0) ts->wcnt[warp] = __popc(bal);
+                        nb_sync(1, FW_MAIN);
+                        int rank = -1;
+                        if (pending) {
+                            int base = 0;
+                            for (int w = 0; w < warp; ++w) base += (int)ts->wcnt[w];
+                            rank = base + __popc(bal & ((1u << lane) - 1u));
+                            ts->iu[rank] = ru; ts->iv[rank] = rv; ts->in[rank] = (uint32_t)n;
+                        }
+                        nb_sync(1, FW_MAIN);
+                        if (warp == 0) {
+                            const bool act = lane < left;
+                            uint32_t xu = act ? ts->iu[lane] : 0u, xv = act ? ts->iv[lane] : 0u;
+                            const uint32_t xn = act ? ts->in[lane] : 0u;
+                            uint32_t yu = 0, yv = 0;
+                            Rec xrec = 0;
+                            bool xp = act;
+                            for (;;) {
+                                if (xp) { st.find2(xu, xv, yu, yv); xp = xu != xv; }
+                                if (!__any_sync(0xffffffffu, xp)) break;
+                                const uint32_t key = (epoch << 10) | (uint32_t)lane;
+                                const uint32_t hub = (uint32_t)sh->hub_key;
+                                const bool star = xp && (xu == hub || xv == hub);
+                                const uint32_t o = xu == hub ? xv : xu, to = xu == hub ? yv : yu;
+                                const uint32_t th = xu == hub ? yu : yv;
+                                uint32_t su = 0, sv = 0;
+                                if (xp) {
+                                    su = claim_slot(star ? o : xu, clog);
+                                    sv = claim_slot(star ? o : xv, clog);
+                                    if (su >= claim_n) su -= claim_n;
+                                    if (sv >= claim_n) sv -= claim_n;
+                                    atomicMin(&claim[su], key);
+                                    if (!star) atomicMin(&claim[sv], key);
+                                }
+                                __syncwarp();
+                                const bool own = xp && claim[su] == key && claim[sv] == key;
+                                const uint32_t blocked = __ballot_sync(0xffffffffu, xp && !own);
+                                const int lb = blocked ? __ffs(blocked) - 1 : 32;
+                                if (own && !star) {
+                                    xrec = make_rec<Rec>(Store::size_m1(yu), Store::size_m1(yv));
+                                    const uint32_t sz = Store::size_m1(yu) + Store::size_m1(yv) + 2;
+                                    const uint32_t m = st.unite(xu, yu, xv, yv, track);
+                                    if (track && (m == 3u || a.any3)) atomicMin(&sh->span_min, xn + 1);
+                                    const uint32_t big = Store::size_m1(yu) >= Store::size_m1(yv) ? xu : xv;
+                                    const unsigned long long hk = ((unsigned long long)sz << 32) | big;
+                                    if (hk > sh->hub_key) atomicMax(&sh->hub_key, hk);
+                                    xp = false;
+                                }
+                                const bool sw = own && star && lane < lb;
+                                if (__any_sync(0xffffffffu, sw)) {
+                                    const uint32_t so = sw ? st.sides_of_root(o, to) : 0u;
+                                    const unsigned long long v =
+                                        sw ? ((unsigned long long)(Store::size_m1(to) + 1) |
+                                              ((unsigned long long)(so & 1u) << 40) |
+                                              ((unsigned long long)(so >> 1) << 50)) : 0ull;
+                                    unsigned long long incl = v;
+#pragma unroll
+                                    for (int k = 1; k < 32; k <<= 1) {
+                                        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, k);
+                                        if (lane >= k) incl += t;
+                                    }
+                                    const unsigned long long total = __shfl_sync(0xffffffffu, incl, 31);
+                                    if (sw) {
+                                        const unsigned long long pre = incl - v;
+                                        const uint32_t hub_m1 = Store::size_m1(th);
+                                        const uint32_t pre_sz = (uint32_t)(pre & 0xffffffffffull);
+                                        xrec = make_rec<Rec>(Store::size_m1(to), hub_m1 + pre_sz);
+                                        st.make_child(o, hub);
+                                        if (track) {
+                                            const uint32_t hs = st.sides_of_root(hub, th);
+                                            const uint32_t m = hs | (((incl >> 40) & 0x3ffu) ? 1u : 0u) |
+                                                               (((incl >> 50) & 0x3ffu) ? 2u : 0u);
+                                            if (m == 3u || a.any3) atomicMin(&sh->span_min, xn + 1);
+                                        }
+                                        if (pre_sz == 0) {
+                                            const uint32_t tot_sz = (uint32_t)(total & 0xffffffffffull);
+                                            const uint32_t add = (((total >> 40) & 0x3ffu) ? 1u : 0u) |
+                                                                 (((total >> 50) & 0x3ffu) ? 2u : 0u);
+                                            st.set_root(hub, hub_m1 + tot_sz, track ? add : 0u);
+                                            atomicMax(&sh->hub_key,
+                                                      ((unsigned long long)(hub_m1 + tot_sz + 1) << 32) | hub);
+                                        }
+                                        xp = false;
+                                    }
+                                }
+                                --epoch;
+                                __syncwarp();
+#ifdef PZ_TIMING
+                                ++fw_trounds;
+#endif
+                            }
+                            if (act) ts->irec[lane] = (unsigned long long)xrec;
+                            if (lane == 0) ts->epoch = epoch;
+                        }
+                        nb_sync(1, FW_MAIN);
+                        epoch = ts->epoch;
+                        if (rank >= 0) rec = (Rec)ts->irec[rank];
+                        pending = false;
+#ifdef PZ_TIMING
+                        fw_tail += clock64() - fw_r0;
+#endif
+                        break;
+                    }
+                    if (!first && pending) {                        // walk up to the new roots
+                        st.find2(ru, rv, tu, tv);
+                        pending = ru != rv;
+                    }
+                    // ---- CTA round.  A warp without pending bonds only takes part in the barriers
                     const bool warp_has = __any_sync(0xffffffffu, pending);
                     const uint32_t key = (epoch << 10) | (uint32_t)tid;
                     uint32_t hub = 0, o = 0, to = 0, th = 0, su = 0, sv = 0;
@@ -874,7 +1009,7 @@ __global__ void __launch_bounds__(FW_ALL + 256, 1) sweep_fw_kernel(SweepArgs a, 
                             else sh->star_epoch = epoch;            // this round needs the star barrier
                         }
                     }
-                    if (!nb_or(1, FW_MAIN, pending)) break;         // nothing (left) to merge
+                    nb_sync(1, FW_MAIN);                            // claims posted
                     const bool star_round = sh->star_epoch == epoch;
                     bool own = false;
                     if (warp_has) {
@@ -945,19 +1080,17 @@ __global__ void __launch_bounds__(FW_ALL + 256, 1) sweep_fw_kernel(SweepArgs a, 
                     if (won) pending = false;
                     --epoch;
                     if (tid == 0) sh->bmin = 0xffffffffu;
-                    if (!nb_or(1, FW_MAIN, pending)) break;         // every candidate merged
-                    if (pending) {                                  // walk up to the new roots
-                        st.find2(ru, rv, tu, tv);
-                        pending = ru != rv;
-                    }
+#ifdef PZ_TIMING
+                    fw_cta += clock64() - fw_r0; ++fw_ncta;
+#endif
                 }
                 if (track && sh->span_min != NSPAN_NEVER) track = false;
                 if (valid) __stcs(&rec_out[n], rec);
             }
 #ifdef PZ_TIMING
             if ((tid & 127) == 0 && blockIdx.x == 0 && run < (int)gridDim.x)
-                printf("fw warp %2d: total %lld, waiting for representatives %lld, walking them up %lld\n",
-                       warp, clock64() - fw_t0, fw_wait, fw_walk);
+                printf("fw warp %2d: total %lld, waiting for representatives %lld, walking them up %lld; %lld CTA rounds %lld cycles; %lld tails (%lld items, %lld warp rounds) %lld cycles\n",
+                       warp, clock64() - fw_t0, fw_wait, fw_walk, fw_ncta, fw_cta, fw_ntail, fw_titems, fw_trounds, fw_tail);
 #endif
         }
         __syncthreads();
@@ -997,7 +1130,10 @@ static SweepPlan plan_team(SweepPlan p, int32_t N, int32_t R, int sms, size_t sm
     if (p.kind == STORE_S16B && CTA_WARPS == 16) {
         int want = 1;
         if (const char *e = getenv("PZ_FINDERS")) want = atoi(e);
-        if (want && clog >= 11) p.finders = 1;      // (the hand-over buffer is carved out of the claim table)
+        if (want && clog >= 11 && align16h(fixed + ((size_t)4 << clog) + 768) <= smem_optin) {
+            p.finders = 1;      // (the hand-over buffer is carved out of the claim table)
+            p.smem_bytes = align16h(fixed + ((size_t)4 << clog) + 768);      // + TailShared
+        }
     }
     p.slice_bytes = p.smem_bytes;
     int ctas_per_sm = (int)(sm_total / (p.smem_bytes + 1024));
