@@ -749,6 +749,9 @@ struct StoreS16BF : StoreS16B {
 
 // (launch bound = the CTA plus one 256-thread CTA of the bond-order kernel: that caps the registers
 // at 72 per thread, so that perm_feistel_kernel of the next chunk still finds room on the SM)
+#ifndef PZ_TAIL_MAX
+#define PZ_TAIL_MAX 32                        // pending bonds at or below which warp 0 finishes the batch
+#endif
 // hand-over area of the tail mode (see below): at most 32 pending bonds of a batch, in batch order
 struct TailShared {
     uint32_t wcnt[FW_MAIN_WARPS];             // pending bonds per main warp
@@ -870,7 +873,7 @@ __global__ void __launch_bounds__(FW_ALL + 256, 1) sweep_fw_kernel(SweepArgs a, 
 #ifdef PZ_TIMING
                     const long long fw_r0 = clock64();
 #endif
-                    if (left <= 32) {
+                    if (left <= PZ_TAIL_MAX) {
 #ifdef PZ_TIMING
                         ++fw_ntail; fw_titems += left;
 #endif
