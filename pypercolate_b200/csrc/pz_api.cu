@@ -291,15 +291,53 @@ int pz_set_graph(pz_ctx *c, int32_t N, int32_t M, const int32_t *eu, const int32
     c->spanning = side_mask != nullptr;
     c->any3 = 0;
 
+    // Global-memory store (N > 65536): the union-find array lives in L2 / HBM and every node visit
+    // is a 32-byte sector.  Node ids are internal (rows carry bond indices only), so nodes are
+    // renumbered by small breadth-first neighbourhoods: the two endpoints of a bond, and a node and
+    // the root of its (small) cluster, then usually share a sector or a line.
+    std::vector<int32_t> relabel;                      // old id -> new id (empty = identity)
+    {
+        int blob = (N > 65536 || c->force_kind == STORE_G32) ? 32 : 0;
+        if (const char *e = getenv("PZ_RELABEL")) blob = atoi(e);
+        if (blob > 1 && M > 0) {
+            std::vector<int64_t> off((size_t)N + 1, 0);
+            for (int32_t e = 0; e < M; ++e) { ++off[(size_t)eu[e] + 1]; ++off[(size_t)ev[e] + 1]; }
+            for (int32_t x = 0; x < N; ++x) off[(size_t)x + 1] += off[x];
+            std::vector<int32_t> adj((size_t)2 * M);
+            {
+                std::vector<int64_t> fill(off.begin(), off.end() - 1);
+                for (int32_t e = 0; e < M; ++e) { adj[fill[eu[e]]++] = ev[e]; adj[fill[ev[e]]++] = eu[e]; }
+            }
+            relabel.assign((size_t)N, -1);
+            std::vector<int32_t> q;
+            q.reserve((size_t)blob);
+            int32_t next = 0;
+            for (int32_t s0 = 0; s0 < N; ++s0) {
+                if (relabel[s0] >= 0) continue;
+                q.clear();
+                q.push_back(s0);
+                relabel[s0] = next++;
+                for (size_t head = 0; head < q.size() && (int)q.size() < blob; ++head) {
+                    const int32_t x = q[head];
+                    for (int64_t k = off[x]; k < off[(size_t)x + 1] && (int)q.size() < blob; ++k) {
+                        const int32_t y = adj[k];
+                        if (relabel[y] < 0) { relabel[y] = next++; q.push_back(y); }
+                    }
+                }
+            }
+        }
+    }
+    auto id = [&](int32_t x) -> uint32_t { return (uint32_t)(relabel.empty() ? x : relabel[x]); };
+
     std::vector<uint2> e64((size_t)std::max(M, 1));
-    for (int32_t e = 0; e < M; ++e) e64[e] = make_uint2((uint32_t)eu[e], (uint32_t)ev[e]);
+    for (int32_t e = 0; e < M; ++e) e64[e] = make_uint2(id(eu[e]), id(ev[e]));
     PZ_CUDA(c->edges64.ensure(e64.size()));
     PZ_CUDA(cudaMemcpyAsync(c->edges64.p, e64.data(), e64.size() * sizeof(uint2),
                             cudaMemcpyHostToDevice, c->stream));
     std::vector<uint32_t> e32;
     if (N <= 65536) {
         e32.resize((size_t)std::max(M, 1));
-        for (int32_t e = 0; e < M; ++e) e32[e] = (uint32_t)eu[e] | ((uint32_t)ev[e] << 16);
+        for (int32_t e = 0; e < M; ++e) e32[e] = id(eu[e]) | (id(ev[e]) << 16);
         PZ_CUDA(c->edges32.ensure(e32.size()));
         PZ_CUDA(cudaMemcpyAsync(c->edges32.p, e32.data(), e32.size() * 4,
                                 cudaMemcpyHostToDevice, c->stream));
@@ -311,7 +349,8 @@ int pz_set_graph(pz_ctx *c, int32_t N, int32_t M, const int32_t *eu, const int32
         for (int32_t x = 0; x < N; ++x) {
             const uint32_t m = side_mask[x] & 3u;
             if (m == 3u) any3 = 1;
-            s2[x >> 4] |= m << ((x & 15) * 2);
+            const uint32_t nx = id(x);
+            s2[nx >> 4] |= m << ((nx & 15) * 2);
         }
         c->any3 = any3;
         PZ_CUDA(c->sides2.ensure(s2.size()));
