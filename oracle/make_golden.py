@@ -4,7 +4,8 @@ reference (``/root/reference/percolate/{percolate,hpc}.py`` through
 ``oracle/ref_shim.py``).  Runs only in the build container (the reference tree
 is not on the GPU box); the fixtures it writes are committed.
 
-    python oracle/make_golden.py
+    python oracle/make_golden.py                     # everything (minutes)
+    python oracle/make_golden.py --only=big_grid256  # just the named fixtures
 
 Every fixture stores its inputs (lowered graph arrays, seeds, ps) next to the
 reference's outputs, so the tests need neither networkx-1.x nor the reference.
@@ -176,9 +177,41 @@ def big_run_fixture(name, L, seeds, p, h):
     print("wrote", name)
 
 
+def original_big_fixture(name, L, seed, p):
+    """One large run through the ORIGINAL api (percolate/percolate.py:103-356: float64
+    moments, global numpy stream): digests of the three per-n columns."""
+    graph = p.spanning_2d_grid(L)
+    np.random.seed(seed)
+    states = list(p.sample_states(graph, spanning_cluster=True, copy_result=True))
+    mx = np.array([s['max_cluster_size'] for s in states], dtype=np.float64)
+    mom = np.stack([np.asarray(s['moments'], dtype=np.float64) for s in states])   # [M+1, 5]
+    span = np.array([s['has_spanning_cluster'] for s in states], dtype=np.uint8)
+    d = dict(L=L, seed=seed, N=states[0]['N'], M=states[0]['M'])
+    for key, arr in (('max', mx), ('moments', mom), ('span', span)):
+        d['sha256_' + key] = np.frombuffer(
+            hashlib.sha256(np.ascontiguousarray(arr).tobytes()).digest(), dtype=np.uint8)
+    d['sample_max'] = mx[::499].copy()
+    d['sample_moments'] = mom[::499].copy()
+    d['sample_span'] = span[::499].copy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print("wrote", name)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     p, h = ref_shim.load()
+    only = None
+    for a in sys.argv[1:]:
+        if a.startswith("--only="):
+            only = set(a[7:].split(","))      # regenerate just these fixtures
+    if only is not None:
+        jobs = {
+            "big_grid256": lambda: big_run_fixture("big_grid256", 256, [3939566288], p, h),
+            "orig_big_grid256": lambda: original_big_fixture("orig_big_grid256", 256, 7, p),
+        }
+        for name in sorted(only):
+            jobs[name]()
+        return
     alpha = p.alpha_1sigma
     ps9 = np.concatenate([np.linspace(0.0, 1.0, 7), [0.45, 0.5]])
 
@@ -204,6 +237,9 @@ def main():
 
     big_run_fixture("big_grid64", 64, [42, 43], p, h)
     big_run_fixture("big_grid128", 128, [42], p, h)
+    # the flagship size (BASELINE config 3), one run through each api of the reference
+    big_run_fixture("big_grid256", 256, [3939566288], p, h)
+    original_big_fixture("orig_big_grid256", 256, 7, p)
 
 
 if __name__ == "__main__":

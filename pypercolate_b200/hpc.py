@@ -27,16 +27,42 @@ from . import _native
 from . import lowering as _lowering
 
 
-def _ndarray_dtype(fields):
-    """
-    Return the NumPy structured array data type
+# Field tables of the four structured types.  The third entry tells whether the field
+# exists only when a spanning cluster is detected.
+_MICRO_FIELDS = (
+    ('n', 'uint32', False), ('edge', 'uint32', False),
+    ('has_spanning_cluster', 'bool', True),
+    ('max_cluster_size', 'uint32', False), ('moments', '(5,)uint64', False),
+)
+_CANON_FIELDS = (
+    ('percolation_probability', 'float64', True),
+    ('max_cluster_size', 'float64', False), ('moments', '(5,)float64', False),
+)
+_AVERAGE_FIELDS = (
+    ('number_of_runs', 'uint32', False),
+    ('percolation_probability_mean', 'float64', True),
+    ('percolation_probability_m2', 'float64', True),
+    ('max_cluster_size_mean', 'float64', False), ('max_cluster_size_m2', 'float64', False),
+    ('moments_mean', '(5,)float64', False), ('moments_m2', '(5,)float64', False),
+)
+_FINAL_FIELDS = (
+    ('number_of_runs', 'uint32', False), ('p', 'float64', False), ('alpha', 'float64', False),
+    ('percolation_probability_mean', 'float64', True),
+    ('percolation_probability_std', 'float64', True),
+    ('percolation_probability_ci', '(2,)float64', True),
+    ('percolation_strength_mean', 'float64', False),
+    ('percolation_strength_std', 'float64', False),
+    ('percolation_strength_ci', '(2,)float64', False),
+    ('moments_mean', '(5,)float64', False), ('moments_std', '(5,)float64', False),
+    ('moments_ci', '(5,2)float64', False),
+)
 
-    Helper function (reference: percolate/hpc.py:22-31)
-    """
-    return [
-        (np.str_(key), values)
-        for key, values in fields
-    ]
+
+def _ndarray_dtype(fields, spanning_cluster=True):
+    """Packed NumPy structured dtype spec (a list of ``(name, type)``) from a
+    field table; same spelling as the reference's helper percolate/hpc.py:22-31."""
+    return [(np.str_(name), kind) for name, kind, span_only in fields
+            if spanning_cluster or not span_only]
 
 
 def microcanonical_statistics_dtype(spanning_cluster=True):
@@ -47,20 +73,7 @@ def microcanonical_statistics_dtype(spanning_cluster=True):
     the spanning flag): ``n:u4, edge:u4, [has_spanning_cluster:?],
     max_cluster_size:u4, moments:(5,)u8``.
     """
-    fields = list()
-    fields.extend([
-        ('n', 'uint32'),
-        ('edge', 'uint32'),
-    ])
-    if spanning_cluster:
-        fields.extend([
-            ('has_spanning_cluster', 'bool'),
-        ])
-    fields.extend([
-        ('max_cluster_size', 'uint32'),
-        ('moments', '(5,)uint64'),
-    ])
-    return _ndarray_dtype(fields)
+    return _ndarray_dtype(_MICRO_FIELDS, spanning_cluster)
 
 
 def _default_device():
@@ -197,16 +210,7 @@ def canonical_statistics_dtype(spanning_cluster=True):
 
     Reference: percolate/hpc.py:407-440.
     """
-    fields = list()
-    if spanning_cluster:
-        fields.extend([
-            ('percolation_probability', 'float64'),
-        ])
-    fields.extend([
-        ('max_cluster_size', 'float64'),
-        ('moments', '(5,)float64'),
-    ])
-    return _ndarray_dtype(fields)
+    return _ndarray_dtype(_CANON_FIELDS, spanning_cluster)
 
 
 _util_ctx = {}
@@ -261,22 +265,7 @@ def canonical_averages_dtype(spanning_cluster=True):
 
     Reference: percolate/hpc.py:518-558.
     """
-    fields = list()
-    fields.extend([
-        ('number_of_runs', 'uint32'),
-    ])
-    if spanning_cluster:
-        fields.extend([
-            ('percolation_probability_mean', 'float64'),
-            ('percolation_probability_m2', 'float64'),
-        ])
-    fields.extend([
-        ('max_cluster_size_mean', 'float64'),
-        ('max_cluster_size_m2', 'float64'),
-        ('moments_mean', '(5,)float64'),
-        ('moments_m2', '(5,)float64'),
-    ])
-    return _ndarray_dtype(fields)
+    return _ndarray_dtype(_AVERAGE_FIELDS, spanning_cluster)
 
 
 def bond_initialize_canonical_averages(
@@ -288,26 +277,15 @@ def bond_initialize_canonical_averages(
     Drop-in for percolate/hpc.py:561-635 (``number_of_runs = 1``, mean = the
     run's value, M2 = 0).  num_p rows of 15 doubles: host arithmetic.
     """
-    spanning_cluster = (
-        'percolation_probability' in canonical_statistics.dtype.names
-    )
-    ret = np.empty_like(
+    names = canonical_statistics.dtype.names
+    out = np.empty_like(
         canonical_statistics,
-        dtype=canonical_averages_dtype(spanning_cluster=spanning_cluster),
-    )
-    ret['number_of_runs'] = 1
-    if spanning_cluster:
-        ret['percolation_probability_mean'] = (
-            canonical_statistics['percolation_probability']
-        )
-        ret['percolation_probability_m2'] = 0.0
-    ret['max_cluster_size_mean'] = (
-        canonical_statistics['max_cluster_size']
-    )
-    ret['max_cluster_size_m2'] = 0.0
-    ret['moments_mean'] = canonical_statistics['moments']
-    ret['moments_m2'] = 0.0
-    return ret
+        dtype=canonical_averages_dtype('percolation_probability' in names))
+    out['number_of_runs'] = 1
+    for name in names:                      # one run: mean = its value, no spread yet
+        out[name + '_mean'] = canonical_statistics[name]
+        out[name + '_m2'] = 0.0
+    return out
 
 
 def _online_variance(n_a, mean_a, m2_a, n_b, mean_b, m2_b):
@@ -332,34 +310,21 @@ def bond_reduce(row_a, row_b):
     Drop-in for percolate/hpc.py:638-702: associative and commutative merge of
     two ``canonical_averages_dtype`` arrays.
     """
-    spanning_cluster = (
-        'percolation_probability_mean' in row_a.dtype.names and
-        'percolation_probability_mean' in row_b.dtype.names and
-        'percolation_probability_m2' in row_a.dtype.names and
-        'percolation_probability_m2' in row_b.dtype.names
-    )
-    ret = np.empty_like(row_a)
-
-    def _reducer(key, transpose=False):
-        mean_key = '{}_mean'.format(key)
-        m2_key = '{}_m2'.format(key)
-        args = []
-        for row in (row_a, row_b):
-            args.extend([
-                row['number_of_runs'],
-                row[mean_key].T if transpose else row[mean_key],
-                row[m2_key].T if transpose else row[m2_key],
-            ])
-        mean, m2 = _online_variance(*args)
-        ret[mean_key] = mean.T if transpose else mean
-        ret[m2_key] = m2.T if transpose else m2
-
-    if spanning_cluster:
-        _reducer('percolation_probability')
-    _reducer('max_cluster_size')
-    _reducer('moments', transpose=True)
-    ret['number_of_runs'] = row_a['number_of_runs'] + row_b['number_of_runs']
-    return ret
+    out = np.empty_like(row_a)
+    stats = ['max_cluster_size', 'moments']
+    if all(key in row.dtype.names for row in (row_a, row_b)
+           for key in ('percolation_probability_mean', 'percolation_probability_m2')):
+        stats.insert(0, 'percolation_probability')
+    n_a, n_b = row_a['number_of_runs'], row_b['number_of_runs']
+    for stat in stats:
+        mean_a, m2_a = row_a[stat + '_mean'], row_a[stat + '_m2']
+        # per-p run counts against (num_p,) or (num_p, 5) statistics
+        shape = n_a.shape + (1,) * (mean_a.ndim - n_a.ndim)
+        out[stat + '_mean'], out[stat + '_m2'] = _online_variance(
+            n_a.reshape(shape), mean_a, m2_a,
+            n_b.reshape(shape), row_b[stat + '_mean'], row_b[stat + '_m2'])
+    out['number_of_runs'] = n_a + n_b
+    return out
 
 
 def finalized_canonical_averages_dtype(spanning_cluster=True):
@@ -369,27 +334,7 @@ def finalized_canonical_averages_dtype(spanning_cluster=True):
 
     Reference: percolate/hpc.py:705-749.
     """
-    fields = list()
-    fields.extend([
-        ('number_of_runs', 'uint32'),
-        ('p', 'float64'),
-        ('alpha', 'float64'),
-    ])
-    if spanning_cluster:
-        fields.extend([
-            ('percolation_probability_mean', 'float64'),
-            ('percolation_probability_std', 'float64'),
-            ('percolation_probability_ci', '(2,)float64'),
-        ])
-    fields.extend([
-        ('percolation_strength_mean', 'float64'),
-        ('percolation_strength_std', 'float64'),
-        ('percolation_strength_ci', '(2,)float64'),
-        ('moments_mean', '(5,)float64'),
-        ('moments_std', '(5,)float64'),
-        ('moments_ci', '(5,2)float64'),
-    ])
-    return _ndarray_dtype(fields)
+    return _ndarray_dtype(_FINAL_FIELDS, spanning_cluster)
 
 
 def finalize_canonical_averages(
@@ -404,55 +349,38 @@ def finalize_canonical_averages(
     percolation probability is not.  scipy is called with the reference's
     arguments, so the quantiles are the reference's by construction.
     """
-    spanning_cluster = (
-        (
-            'percolation_probability_mean' in
-            canonical_averages.dtype.names
-        ) and
-        'percolation_probability_m2' in canonical_averages.dtype.names
-    )
-    ret = np.empty_like(
+    names = canonical_averages.dtype.names
+    spanning_cluster = ('percolation_probability_mean' in names and
+                        'percolation_probability_m2' in names)
+    out = np.empty_like(
         canonical_averages,
-        dtype=finalized_canonical_averages_dtype(
-            spanning_cluster=spanning_cluster
-        ),
-    )
-    n = canonical_averages['number_of_runs']
-    sqrt_n = np.sqrt(canonical_averages['number_of_runs'])
-    ret['number_of_runs'] = n
-    ret['p'] = ps
-    ret['alpha'] = alpha
+        dtype=finalized_canonical_averages_dtype(spanning_cluster))
+    runs = canonical_averages['number_of_runs']
+    out['number_of_runs'] = runs
+    out['p'] = ps
+    out['alpha'] = alpha
 
-    def _transform(original_key, final_key=None, normalize=False,
-                   transpose=False):
-        if final_key is None:
-            final_key = original_key
-        mean = canonical_averages['{}_mean'.format(original_key)]
-        ret['{}_mean'.format(final_key)] = mean
-        if normalize:
-            ret['{}_mean'.format(final_key)] /= number_of_nodes
-        array = canonical_averages['{}_m2'.format(original_key)]
-        with np.errstate(divide='ignore', invalid='ignore'):
-            result = np.sqrt((array.T if transpose else array) / (n - 1))
-        ret['{}_std'.format(final_key)] = result.T if transpose else result
-        if normalize:
-            ret['{}_std'.format(final_key)] /= number_of_nodes
-        array = ret['{}_std'.format(final_key)]
-        scale = (array.T if transpose else array) / sqrt_n
-        array = ret['{}_mean'.format(final_key)]
-        loc = (array.T if transpose else array)
-        with np.errstate(divide='ignore', invalid='ignore'):
-            result = scipy.stats.t.interval(1 - alpha, df=n - 1, loc=loc,
-                                            scale=scale)
-        key_ci = '{}_ci'.format(final_key)
-        (ret[key_ci][..., 0], ret[key_ci][..., 1]) = (
-            [my_array.T for my_array in result] if transpose else result)
-
+    # (input statistic, output statistic, reported per node?)
+    plan = [('max_cluster_size', 'percolation_strength', True), ('moments', 'moments', True)]
     if spanning_cluster:
-        _transform('percolation_probability')
-    _transform('max_cluster_size', 'percolation_strength', normalize=True)
-    _transform('moments', normalize=True, transpose=True)
-    return ret
+        plan.insert(0, ('percolation_probability', 'percolation_probability', False))
+    for src, dst, per_node in plan:
+        mean = out[dst + '_mean']
+        std = out[dst + '_std']
+        # run counts broadcast against (num_p,) or (num_p, 5) statistics
+        n = runs.reshape(runs.shape + (1,) * (mean.ndim - runs.ndim))
+        mean[...] = canonical_averages[src + '_mean']
+        with np.errstate(divide='ignore', invalid='ignore'):
+            std[...] = np.sqrt(canonical_averages[src + '_m2'] / (n - 1))
+        if per_node:
+            mean /= number_of_nodes
+            std /= number_of_nodes
+        with np.errstate(divide='ignore', invalid='ignore'):
+            lo, hi = scipy.stats.t.interval(1 - alpha, df=n - 1, loc=mean,
+                                            scale=std / np.sqrt(n))
+        out[dst + '_ci'][..., 0] = lo
+        out[dst + '_ci'][..., 1] = hi
+    return out
 
 
 # ---------------------------------------------------------------------------

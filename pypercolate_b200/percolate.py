@@ -43,50 +43,31 @@ def percolation_graph(graph, spanning_cluster=True):
     ValueError
         no auxiliary nodes, or not exactly two spanning sides
     """
-    ret = dict()
-
-    ret['graph'] = graph
-    ret['spanning_cluster'] = bool(spanning_cluster)
-
+    real = graph
+    out = {'graph': graph, 'spanning_cluster': bool(spanning_cluster)}
     if spanning_cluster:
-        spanning_auxiliary_node_attributes = nx.get_node_attributes(
-            graph, 'span'
-        )
-        ret['auxiliary_node_attributes'] = spanning_auxiliary_node_attributes
-        auxiliary_nodes = spanning_auxiliary_node_attributes.keys()
-        if not list(auxiliary_nodes):
+        aux = nx.get_node_attributes(graph, 'span')        # auxiliary node -> side
+        if len(aux) == 0:
             raise ValueError(
                 'Spanning cluster is to be detected, but no auxiliary nodes '
                 'given.'
             )
-
-        spanning_sides = list(set(spanning_auxiliary_node_attributes.values()))
-        if len(spanning_sides) != 2:
+        sides = list(set(aux.values()))
+        if len(sides) != 2:
             raise ValueError(
                 'Spanning cluster is to be detected, but auxiliary nodes '
                 'of less or more than 2 types (sides) given.'
             )
-
-        ret['spanning_sides'] = spanning_sides
-        ret['auxiliary_edge_attributes'] = nx.get_edge_attributes(
-            graph, 'span'
+        out.update(
+            auxiliary_node_attributes=aux,
+            spanning_sides=sides,
+            auxiliary_edge_attributes=nx.get_edge_attributes(graph, 'span'),
         )
-
-    if spanning_cluster:
-        perc_graph = graph.subgraph(
-            [
-                node for node in graph.nodes
-                if 'span' not in graph.nodes[node]
-            ]
-        )
-    else:
-        perc_graph = graph
-
-    ret['perc_graph'] = perc_graph
-    ret['num_nodes'] = nx.number_of_nodes(perc_graph)
-    ret['num_edges'] = nx.number_of_edges(perc_graph)
-
-    return ret
+        # the real lattice: everything that is not an auxiliary node
+        real = graph.subgraph([v for v in graph.nodes if v not in aux])
+    out.update(perc_graph=real, num_nodes=real.number_of_nodes(),
+               num_edges=real.number_of_edges())
+    return out
 
 
 _GRAPH_CACHE_ATTR = '_pz_percolation'
@@ -204,39 +185,31 @@ def single_run_arrays(spanning_cluster=True, **kwargs):
     ``has_spanning_cluster`` (bool[M+1], only if ``spanning_cluster``),
     ``N`` and ``M``.
     '''
-    kwargs['copy_result'] = False
-    ret = dict()
+    states = sample_states(spanning_cluster=spanning_cluster,
+                           **dict(kwargs, copy_result=False))
+    first = next(states)
+    num_nodes, num_edges = first['N'], first['M']
+    largest = np.empty(num_edges + 1)
+    moments = np.empty((5, num_edges + 1))
+    spans = np.empty(num_edges + 1, dtype=bool) if spanning_cluster else None
 
-    for n, state in enumerate(sample_states(
-        spanning_cluster=spanning_cluster, **kwargs
-    )):
-        if 'N' in ret:
-            assert ret['N'] == state['N']
-        else:
-            ret['N'] = state['N']
+    def store(state):
+        assert (state['N'], state['M']) == (num_nodes, num_edges)
+        n = state['n']
+        largest[n] = state['max_cluster_size']
+        moments[:, n] = state['moments']
+        if spans is not None:
+            spans[n] = state['has_spanning_cluster']
 
-        if 'M' in ret:
-            assert ret['M'] == state['M']
-        else:
-            ret['M'] = state['M']
-            number_of_states = state['M'] + 1
-            max_cluster_size = np.empty(number_of_states)
-            if spanning_cluster:
-                has_spanning_cluster = np.empty(number_of_states, dtype=bool)
-            moments = np.empty((5, number_of_states))
+    store(first)
+    for state in states:
+        store(state)
 
-        max_cluster_size[n] = state['max_cluster_size']
-        for k in range(5):
-            moments[k, n] = state['moments'][k]
-        if spanning_cluster:
-            has_spanning_cluster[n] = state['has_spanning_cluster']
-
-    ret['max_cluster_size'] = max_cluster_size
-    ret['moments'] = moments
-    if spanning_cluster:
-        ret['has_spanning_cluster'] = has_spanning_cluster
-
-    return ret
+    out = {'N': num_nodes, 'M': num_edges, 'max_cluster_size': largest,
+           'moments': moments}
+    if spans is not None:
+        out['has_spanning_cluster'] = spans
+    return out
 
 
 def _microcanonical_average_spanning_cluster(has_spanning_cluster, alpha):
@@ -247,17 +220,23 @@ def _microcanonical_average_spanning_cluster(has_spanning_cluster, alpha):
     ``(k + 1) / (runs + 2)`` and the ``1 - alpha`` credible interval
     ``beta.ppf([alpha/2, 1 - alpha/2], k + 1, runs - k + 1)``.
     '''
-    ret = dict()
     runs = has_spanning_cluster.size
-
     k = has_spanning_cluster.sum(dtype=float)
-    ret['spanning_cluster'] = (
-        (k + 1) / (runs + 2)
-    )
-    ret['spanning_cluster_ci'] = scipy.stats.beta.ppf(
-        [alpha / 2, 1 - alpha / 2], k + 1, runs - k + 1
-    )
-    return ret
+    tails = [alpha / 2, 1 - alpha / 2]
+    return {
+        'spanning_cluster': (k + 1) / (runs + 2),
+        'spanning_cluster_ci': scipy.stats.beta.ppf(tails, k + 1, runs - k + 1),
+    }
+
+
+def _t_interval_or_point(mean, std, runs, alpha):
+    """Student-t ``1 - alpha`` interval of a sample mean; the degenerate
+    ``(mean, mean)`` when the sample standard deviation is zero
+    (percolate/percolate.py:621-633, 691-703)."""
+    if not std:
+        return mean * np.ones(2)
+    return scipy.stats.t.interval(1 - alpha, df=runs - 1, loc=mean,
+                                  scale=std / np.sqrt(runs))
 
 
 def _microcanonical_average_max_cluster_size(max_cluster_size, alpha):
@@ -267,26 +246,13 @@ def _microcanonical_average_max_cluster_size(max_cluster_size, alpha):
     Drop-in for percolate/percolate.py:575-635: sample mean and Student-t
     ``1 - alpha`` interval; ``(mean, mean)`` when the sample std is zero.
     """
-    ret = dict()
-    runs = max_cluster_size.size
-    sqrt_n = np.sqrt(runs)
-
-    max_cluster_size_sample_mean = max_cluster_size.mean()
-    ret['max_cluster_size'] = max_cluster_size_sample_mean
-
-    max_cluster_size_sample_std = max_cluster_size.std(ddof=1)
-    if max_cluster_size_sample_std:
-        ret['max_cluster_size_ci'] = scipy.stats.t.interval(
-            1 - alpha,
-            df=runs - 1,
-            loc=max_cluster_size_sample_mean,
-            scale=max_cluster_size_sample_std / sqrt_n
-        )
-    else:
-        ret['max_cluster_size_ci'] = (
-            max_cluster_size_sample_mean * np.ones(2)
-        )
-    return ret
+    mean = max_cluster_size.mean()
+    std = max_cluster_size.std(ddof=1)
+    return {
+        'max_cluster_size': mean,
+        'max_cluster_size_ci': _t_interval_or_point(
+            mean, std, max_cluster_size.size, alpha),
+    }
 
 
 def _microcanonical_average_moments(moments, alpha):
@@ -296,28 +262,13 @@ def _microcanonical_average_moments(moments, alpha):
     Drop-in for percolate/percolate.py:638-705 (``moments`` has shape
     ``(runs, 5)``).
     """
-    ret = dict()
     runs = moments.shape[0]
-    sqrt_n = np.sqrt(runs)
-
-    moments_sample_mean = moments.mean(axis=0)
-    ret['moments'] = moments_sample_mean
-
-    moments_sample_std = moments.std(axis=0, ddof=1)
-    ret['moments_ci'] = np.empty((5, 2))
+    mean = moments.mean(axis=0)
+    std = moments.std(axis=0, ddof=1)
+    ci = np.empty((5, 2))
     for k in range(5):
-        if moments_sample_std[k]:
-            ret['moments_ci'][k] = scipy.stats.t.interval(
-                1 - alpha,
-                df=runs - 1,
-                loc=moments_sample_mean[k],
-                scale=moments_sample_std[k] / sqrt_n
-            )
-        else:
-            ret['moments_ci'][k] = (
-                moments_sample_mean[k] * np.ones(2)
-            )
-    return ret
+        ci[k] = _t_interval_or_point(mean[k], std[k], runs, alpha)
+    return {'moments': mean, 'moments_ci': ci}
 
 
 # credible intervals already evaluated, per (runs, alpha): [known[k], lo[k], hi[k]] for k = 0..runs
@@ -534,14 +485,12 @@ def spanning_1d_chain(length):
 
     Drop-in for percolate/percolate.py:899-928 (networkx >= 2 spelling).
     """
-    ret = nx.grid_graph(dim=[int(length + 2)])
-
-    ret.nodes[0]['span'] = 0
-    ret[0][1]['span'] = 0
-    ret.nodes[length + 1]['span'] = 1
-    ret[length][length + 1]['span'] = 1
-
-    return ret
+    length = int(length)
+    chain = nx.path_graph(length + 2)           # nodes 0 .. length + 1
+    ends = {0: (0, 1), 1: (length + 1, length)}   # side -> (auxiliary node, its neighbour)
+    nx.set_node_attributes(chain, {aux: side for side, (aux, _) in ends.items()}, 'span')
+    nx.set_edge_attributes(chain, {pair: side for side, pair in ends.items()}, 'span')
+    return chain
 
 
 def spanning_2d_grid(length):
@@ -550,18 +499,15 @@ def spanning_2d_grid(length):
 
     Drop-in for percolate/percolate.py:931-965 (networkx >= 2 spelling).
     """
-    ret = nx.grid_2d_graph(length + 2, length)
-
-    for i in range(length):
-        # side 0
-        ret.nodes[(0, i)]['span'] = 0
-        ret[(0, i)][(1, i)]['span'] = 0
-
-        # side 1
-        ret.nodes[(length + 1, i)]['span'] = 1
-        ret[(length + 1, i)][(length, i)]['span'] = 1
-
-    return ret
+    grid = nx.grid_2d_graph(length + 2, length)
+    # columns 0 and length + 1 are auxiliary; each is tied to the lattice column next to it
+    columns = {0: (0, 1), 1: (length + 1, length)}          # side -> (aux column, lattice column)
+    nx.set_node_attributes(
+        grid, {(aux, i): side for side, (aux, _) in columns.items() for i in range(length)}, 'span')
+    nx.set_edge_attributes(
+        grid, {((aux, i), (real, i)): side
+               for side, (aux, real) in columns.items() for i in range(length)}, 'span')
+    return grid
 
 
 def microcanonical_averages_arrays(microcanonical_averages):
@@ -584,43 +530,30 @@ def microcanonical_averages_arrays(microcanonical_averages):
             ret[key] = np.array(value, dtype=np.float64, copy=True)
         # the reference's layout: moments (5, M+1), moments_ci (5, M+1, 2)
     else:
-        for n, microcanonical_average in enumerate(microcanonical_averages):
-            assert n == microcanonical_average['n']
+        # any iterable of per-n dictionaries: collect, then stack
+        cols = {}
+        count = 0
+        for n, avg in enumerate(microcanonical_averages):
+            assert n == avg['n']
             if n == 0:
-                num_edges = microcanonical_average['M']
-                num_sites = microcanonical_average['N']
-                spanning_cluster = ('spanning_cluster' in microcanonical_average)
-                ret['max_cluster_size'] = np.empty(num_edges + 1)
-                ret['max_cluster_size_ci'] = np.empty((num_edges + 1, 2))
+                num_edges, num_sites = avg['M'], avg['N']
+                cols = {key: [] for key in avg if key.split('_ci')[0] in
+                        ('max_cluster_size', 'spanning_cluster', 'moments')}
+            for key, seq in cols.items():
+                seq.append(np.array(avg[key], dtype=np.float64))
+            count = n + 1
+        assert count == num_edges + 1
+        for key, seq in cols.items():
+            stacked = np.stack(seq)                         # n first
+            # the reference's layout: moments (5, M+1), moments_ci (5, M+1, 2)
+            ret[key] = np.ascontiguousarray(np.moveaxis(stacked, 0, 1)) \
+                if key.startswith('moments') else stacked
 
-                if spanning_cluster:
-                    ret['spanning_cluster'] = np.empty(num_edges + 1)
-                    ret['spanning_cluster_ci'] = np.empty((num_edges + 1, 2))
-
-                ret['moments'] = np.empty((5, num_edges + 1))
-                ret['moments_ci'] = np.empty((5, num_edges + 1, 2))
-
-            ret['max_cluster_size'][n] = microcanonical_average['max_cluster_size']
-            ret['max_cluster_size_ci'][n] = (
-                microcanonical_average['max_cluster_size_ci']
-            )
-
-            if spanning_cluster:
-                ret['spanning_cluster'][n] = (
-                    microcanonical_average['spanning_cluster']
-                )
-                ret['spanning_cluster_ci'][n] = (
-                    microcanonical_average['spanning_cluster_ci']
-                )
-
-            ret['moments'][:, n] = microcanonical_average['moments']
-            ret['moments_ci'][:, n] = microcanonical_average['moments_ci']
-
-    # normalize by number of sites
-    for key in ret:
-        if 'spanning_cluster' in key:
-            continue
-        ret[key] /= num_sites
+    # everything but the spanning probability is reported per site
+    # (percolate/percolate.py:1056-1060)
+    for key, value in ret.items():
+        if 'spanning_cluster' not in key:
+            value /= num_sites
 
     ret['M'] = num_edges
     ret['N'] = num_sites
@@ -650,24 +583,16 @@ def canonical_averages(ps, microcanonical_averages_arrays):
     weights and the ``[num_p x (M+1)] . [(M+1) x columns]`` contraction are
     computed on the GPU.
     """
-    num_sites = microcanonical_averages_arrays['N']
-    num_edges = microcanonical_averages_arrays['M']
-    spanning_cluster = ('spanning_cluster' in microcanonical_averages_arrays)
-
-    ret = dict()
-    ret['ps'] = ps
-    ret['N'] = num_sites
-    ret['M'] = num_edges
-
-    ret['max_cluster_size'] = np.empty(ps.size)
-    ret['max_cluster_size_ci'] = np.empty((ps.size, 2))
-
-    if spanning_cluster:
-        ret['spanning_cluster'] = np.empty(ps.size)
-        ret['spanning_cluster_ci'] = np.empty((ps.size, 2))
-
-    ret['moments'] = np.empty((5, ps.size))
-    ret['moments_ci'] = np.empty((5, ps.size, 2))
+    arrays = microcanonical_averages_arrays
+    num_edges = arrays['M']
+    num_p = ps.size
+    ret = {'ps': ps, 'N': arrays['N'], 'M': num_edges}
+    # output shapes: the n axis of every input array becomes the p axis
+    for key, shape in (('max_cluster_size', (num_p,)), ('max_cluster_size_ci', (num_p, 2)),
+                       ('spanning_cluster', (num_p,)), ('spanning_cluster_ci', (num_p, 2)),
+                       ('moments', (5, num_p)), ('moments_ci', (5, num_p, 2))):
+        if key in arrays:
+            ret[key] = np.empty(shape)
 
     # gather every column of length M+1, contract once, scatter back
     columns = []
@@ -718,13 +643,6 @@ def statistics(
     ``microcanonical_averages`` -> ``microcanonical_averages_arrays`` ->
     ``canonical_averages``.
     """
-    my_microcanonical_averages = microcanonical_averages(
-        graph=graph, runs=runs, spanning_cluster=spanning_cluster, model=model,
-        alpha=alpha
-    )
-
-    my_microcanonical_averages_arrays = microcanonical_averages_arrays(
-        my_microcanonical_averages
-    )
-
-    return canonical_averages(ps, my_microcanonical_averages_arrays)
+    per_n = microcanonical_averages_arrays(microcanonical_averages(
+        graph=graph, runs=runs, spanning_cluster=spanning_cluster, model=model, alpha=alpha))
+    return canonical_averages(ps, per_n)

@@ -60,7 +60,7 @@ def test_rows_match_reference_golden(name, force):
     ctx.close()
 
 
-@pytest.mark.parametrize("name", ["big_grid64", "big_grid128"])
+@pytest.mark.parametrize("name", ["big_grid64", "big_grid128", "big_grid256"])
 def test_large_single_runs_match_reference_digest(name):
     from pypercolate_b200 import lowering
     n = _native()
@@ -401,6 +401,24 @@ def test_original_api_matches_reference_golden(name):
     assert single['moments'].shape == (5, g.num_edges + 1)
     if spanning:
         assert np.array_equal(single['has_spanning_cluster'], d['states_span'])
+
+
+def test_original_api_large_run_matches_reference_digest():
+    """One L = 256 run through ``single_run_arrays`` (global numpy stream, float64 moments) against
+    the digests of the unmodified reference's ``sample_states`` (tests/golden/orig_big_grid256)."""
+    from pypercolate_b200 import lowering, percolate
+    d = load_golden("orig_big_grid256")
+    g = lowering.lowered_spanning_2d_grid(int(d['L']))
+    np.random.seed(int(d['seed']))
+    single = percolate.single_run_arrays(graph=g, spanning_cluster=True)
+    assert (single['N'], single['M']) == (int(d['N']), int(d['M']))
+    cols = {'max': single['max_cluster_size'],
+            'moments': np.ascontiguousarray(single['moments'].T),
+            'span': single['has_spanning_cluster'].astype(np.uint8)}
+    for key, arr in cols.items():
+        assert arr.dtype == d['sample_' + key].dtype, key
+        assert np.array_equal(arr[::499], d['sample_' + key]), key
+        assert hashlib.sha256(arr.tobytes()).digest() == d['sha256_' + key].tobytes(), key
 
 
 def test_microcanonical_averages_initial_iteration():
