@@ -310,7 +310,7 @@ def main():
             "e2e": {
                 "value": e2e_value, "unit": UNIT,
                 "h2d_bytes_per_step": int(seeds_host.nbytes + ps.nbytes),
-                "d2h_bytes_per_step": int(13 * (M + 1) * 8 + 2 * NUM_P * 7 * 8),
+                "d2h_bytes_per_step": int(19 * (M + 1) * 8 + 2 * NUM_P * 7 * 8),   # pz_micro_arrays + canonical partials
                 "ms_per_step": e2e_ms / args.steps,
                 "api": "pypercolate_b200.hpc.bond_statistics_batch (host seeds/ps in, "
                        "microcanonical arrays + finalized canonical averages out)",

@@ -150,6 +150,22 @@ int pz_micro_import(pz_ctx *ctx, const uint64_t *src, int is_device, int64_t run
 int pz_micro_finalize(pz_ctx *ctx, double *mean_out, double *var_out);
 
 /*
+ * The arrays of microcanonical_averages_arrays (percolate/percolate.py:968-1064)
+ * straight from the exact sums: per-n sample mean and Student-t interval
+ * t * std / sqrt(runs) + mean, (mean, mean) when the sample std is zero
+ * (percolate/percolate.py:613-635, 681-705), each divided by norm (the number of
+ * sites for the reference's normalisation, percolate/percolate.py:1056-1060; 1.0
+ * for none).  t_lo, t_hi = scipy.stats.t.interval(1 - alpha, df = runs - 1), taken
+ * once by the caller.  Separately rounded IEEE operations in numpy's order: the
+ * result is bit-identical to evaluating the same formulas on the host.
+ *   out  host double[19 * S], S = M + 1:
+ *        [0, S) runs spanning at n (k, not divided) | [S, 2S) max_cluster_size |
+ *        [2S, 4S) max_cluster_size_ci[S][2] | [4S, 14S) moments_ci[5][S][2] |
+ *        [14S, 19S) moments[5][S]
+ */
+int pz_micro_arrays(pz_ctx *ctx, double t_lo, double t_hi, double norm, double *out);
+
+/*
  * Binomial weights: replaces _binomial_pmf (percolate/percolate.py:1067-1109),
  * one p per thread, the reference's mode-outward ratio recurrence in the
  * reference's operation order, for M bonds (no graph needed).  pmf_out: host

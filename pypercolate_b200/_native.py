@@ -30,7 +30,7 @@ SYMBOLS = [
     "pz_last_error", "pz_version", "pz_create", "pz_destroy", "pz_device",
     "pz_stream", "pz_synchronize", "pz_set_graph", "pz_row_bytes",
     "pz_run_rows", "pz_run_fused", "pz_reset_accumulators", "pz_micro_runs",
-    "pz_micro_export", "pz_micro_import", "pz_micro_finalize", "pz_set_ps",
+    "pz_micro_export", "pz_micro_import", "pz_micro_finalize", "pz_micro_arrays", "pz_set_ps",
     "pz_convolve", "pz_canonical_statistics_rows", "pz_canon_export",
     "pz_canon_merge", "pz_canon_last_runs", "pz_launch_count",
     "pz_make_perms", "pz_profile", "pz_profile_read", "pz_canon_reset", "pz_timer_start", "pz_timer_stop",
@@ -82,6 +82,7 @@ def load():
         L.pz_micro_export.argtypes = [vp, vp, ci]
         L.pz_micro_import.argtypes = [vp, vp, ci, i64]
         L.pz_micro_finalize.argtypes = [vp, vp, vp]
+        L.pz_micro_arrays.argtypes = [vp, ctypes.c_double, ctypes.c_double, ctypes.c_double, vp]
         L.pz_set_ps.argtypes = [vp, i32, i32, vp, vp]
         L.pz_convolve.argtypes = [vp, i32, vp, vp]
         L.pz_canonical_statistics_rows.argtypes = [vp, i32, ci, vp, vp, vp]
@@ -227,6 +228,15 @@ class Context(object):
         var = np.empty((6, self.M + 1), dtype=np.float64)
         _check(self._L.pz_micro_finalize(self._h, _ptr(mean), _ptr(var)))
         return mean, var
+
+    def micro_arrays(self, t_lo, t_hi, norm=1.0):
+        """Per-n means and Student-t intervals, divided by ``norm``, as views of one
+        host buffer: ``k[S], max[S], max_ci[S, 2], moments[5, S], moments_ci[5, S, 2]``."""
+        S = self.M + 1
+        buf = np.empty(19 * S, dtype=np.float64)
+        _check(self._L.pz_micro_arrays(self._h, float(t_lo), float(t_hi), float(norm), _ptr(buf)))
+        return (buf[:S], buf[S:2 * S], buf[2 * S:4 * S].reshape(S, 2),
+                buf[14 * S:].reshape(5, S), buf[4 * S:14 * S].reshape(5, S, 2))
 
     def micro_finalize_device_only(self):
         _check(self._L.pz_micro_finalize(self._h, None, None))

@@ -95,6 +95,7 @@ struct pz_ctx {
     DevBuf<unsigned long long> acc;       // (M+1) * PZ_ACC_WORDS
     DevBuf<unsigned long long> span_cum;  // M + 1
     DevBuf<double> fin;                   // 13 * (M+1): mean[7], var[6]
+    DevBuf<double> arrays;                // 19 * (M+1): pz_micro_arrays
     int64_t micro_runs = 0;
     int ckpt_every = 64;                  // run state checkpoints every so many rows (64 = tile
                                           // form of accumulate; PZ_CKPT_EVERY=1024: segment form)
@@ -169,6 +170,8 @@ cudaError_t launch_accumulate(const StatsArgs &a, unsigned long long *acc, const
 cudaError_t launch_micro_finalize(int32_t N, int32_t M, int64_t runs, const unsigned long long *acc,
                                   unsigned long long *span_cum, double *mean, double *var,
                                   cudaStream_t s);
+cudaError_t launch_micro_arrays(int32_t M, int64_t runs, double t_lo, double t_hi, double norm,
+                                const double *mean, const double *var, double *out, cudaStream_t s);
 cudaError_t launch_binomial_pmf(int32_t M, int32_t P, const double *ps_dev, double *pmf,
                                 int32_t *xlo, int32_t *xhi, int32_t *tlo, int32_t *thi, double *sf,
                                 cudaStream_t s);
@@ -250,7 +253,7 @@ void pz_destroy(pz_ctx *c)
     }
     c->perm_super.release(); c->seed_super.release();
     c->gscratch.release(); c->rows.release(); c->acc.release(); c->span_cum.release();
-    c->fin.release(); c->ps_dev.release(); c->band_lo.release();
+    c->fin.release(); c->arrays.release(); c->ps_dev.release(); c->band_lo.release();
     c->band_hi.release(); c->tband_lo.release(); c->tband_hi.release(); c->canon_flags.release();
     c->sf.release(); c->porder_dev.release(); c->cols.release(); c->cols_out.release();
     c->pmf.release();
@@ -800,6 +803,21 @@ int pz_micro_finalize(pz_ctx *c, double *mean_out, double *var_out)
         PZ_CUDA(cudaMemcpyAsync(mean_out, c->fin.p, 7 * S * 8, cudaMemcpyDeviceToHost, c->stream));
         PZ_CUDA(cudaMemcpyAsync(var_out, c->fin.p + 7 * S, 6 * S * 8, cudaMemcpyDeviceToHost, c->stream));
     }
+    PZ_CUDA(cudaStreamSynchronize(c->stream));
+    return PZ_OK;
+}
+
+int pz_micro_arrays(pz_ctx *c, double t_lo, double t_hi, double norm, double *out)
+{
+    if (!c || !out || !(norm > 0.0)) return fail(PZ_ERR_ARG, "pz_micro_arrays: bad arguments");
+    int rc = pz_micro_finalize(c, nullptr, nullptr);        // mean / var stay on the device
+    if (rc) return rc;
+    const size_t S = (size_t)c->M + 1;
+    PZ_CUDA(c->arrays.ensure(19 * S));
+    PZ_CUDA(launch_micro_arrays(c->M, c->micro_runs, t_lo, t_hi, norm, c->fin.p, c->fin.p + 7 * S,
+                                c->arrays.p, c->stream));
+    c->launches += 1;
+    PZ_CUDA(cudaMemcpyAsync(out, c->arrays.p, 19 * S * 8, cudaMemcpyDeviceToHost, c->stream));
     PZ_CUDA(cudaStreamSynchronize(c->stream));
     return PZ_OK;
 }

@@ -676,6 +676,48 @@ cudaError_t launch_micro_finalize(int32_t N, int32_t M, int64_t runs, const unsi
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------
+// micro_arrays: the per-n arrays of microcanonical_averages_arrays
+// (percolate/percolate.py:968-1064) from mean[7][S] / var[6][S]: sample mean and
+// Student-t interval  t * std / sqrt(runs) + mean  (percolate/percolate.py:613-635,
+// 681-705; (mean, mean) when the sample std is zero), each divided by `norm`
+// (the number of sites, percolate/percolate.py:1056-1060).  Every operation is a
+// separately rounded IEEE double operation in the order numpy performs them on the
+// host, so the arrays are bit-identical to the host evaluation they replace.
+// out: k[S] | max[S] | max_ci[S][2] | moments_ci[5][S][2] | moments[5][S]   (the interval
+// blocks start at even offsets, so that their double2 stores are aligned for odd S too)
+// ---------------------------------------------------------------------------
+__global__ void micro_arrays_kernel(int32_t M, double sqrt_runs, double t_lo, double t_hi, double norm,
+                                    const double *mean, const double *var, double *out)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n > M) return;
+    const size_t S = (size_t)M + 1;
+    out[n] = mean[n];                                       // runs spanning at n
+    double *mx = out + S, *mom = out + 14 * S;
+    double2 *mx_ci = reinterpret_cast<double2 *>(out + 2 * S);
+    double2 *mom_ci = reinterpret_cast<double2 *>(out + 4 * S);
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {                           // 0: max, 1..5: moments[0..4]
+        const double m = mean[(size_t)(1 + q) * S + n];
+        const double sd = sqrt(var[(size_t)q * S + n]);
+        const double scale = __ddiv_rn(sd, sqrt_runs);
+        double lo = __dadd_rn(__dmul_rn(t_lo, scale), m), hi = __dadd_rn(__dmul_rn(t_hi, scale), m);
+        if (sd == 0.0) { lo = m; hi = m; }
+        const double2 ci = make_double2(__ddiv_rn(lo, norm), __ddiv_rn(hi, norm));
+        if (q == 0) { mx[n] = __ddiv_rn(m, norm); mx_ci[n] = ci; }
+        else { mom[(size_t)(q - 1) * S + n] = __ddiv_rn(m, norm); mom_ci[(size_t)(q - 1) * S + n] = ci; }
+    }
+}
+
+cudaError_t launch_micro_arrays(int32_t M, int64_t runs, double t_lo, double t_hi, double norm,
+                                const double *mean, const double *var, double *out, cudaStream_t s)
+{
+    const int grid = (M + 1 + 127) / 128;
+    micro_arrays_kernel<<<grid, 128, 0, s>>>(M, sqrt((double)runs), t_lo, t_hi, norm, mean, var, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_expand_rows(const StatsArgs &a, uint8_t *rows, cudaStream_t s)
 {
     if (a.R <= 0) return cudaSuccess;

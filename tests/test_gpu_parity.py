@@ -456,6 +456,38 @@ def test_fused_hpc_batch_equals_reference_map_reduce():
         np.testing.assert_allclose(got[f], ref[f], rtol=1e-9, atol=1e-13 * scale)
 
 
+def test_device_micro_arrays_equal_host_evaluation():
+    """pz_micro_arrays (means, Student-t intervals, per-site normalisation on the device) is
+    bit-identical to the host formulas of percolate._arrays_from_device + the division by N
+    (percolate/percolate.py:613-635, 681-705, 1056-1060), including the zero-variance rows."""
+    import scipy.stats
+    from pypercolate_b200 import lowering, percolate
+    n = _native()
+    for L, runs, alpha in ((8, 70, 0.05), (32, 40, percolate.alpha_1sigma), (5, 1, 0.3)):
+        g = lowering.lowered_spanning_2d_grid(L)
+        ctx = ctx_for(g)
+        ctx.reset_accumulators()
+        ctx.run_fused(runs, n.PERM_MT19937, np.arange(runs, dtype=np.uint32) + 17, n.FUSE_MICRO)
+        mean, var = ctx.micro_finalize()
+        host = percolate._arrays_from_device(mean, var, runs, alpha, g.num_nodes, g.num_edges, True)
+        with np.errstate(invalid='ignore'):
+            t_lo, t_hi = scipy.stats.t.interval(1 - alpha, df=runs - 1)
+        k, mx, mx_ci, mom, mom_ci = ctx.micro_arrays(t_lo, t_hi, norm=g.num_nodes)
+        assert np.array_equal(k, mean[0])
+        for dev, key in ((mx, 'max_cluster_size'), (mx_ci, 'max_cluster_size_ci'),
+                         (mom, 'moments'), (mom_ci, 'moments_ci')):
+            want = host[key] / g.num_nodes
+            assert dev.shape == want.shape, key
+            assert np.array_equal(dev, want, equal_nan=True), (L, runs, key)
+        if runs > 1:
+            assert (var[0] == 0).any() and np.array_equal(mx_ci[var[0] == 0, 0], mx[var[0] == 0])
+        _, mx1, mx1_ci, _, _ = ctx.micro_arrays(t_lo, t_hi)              # norm = 1
+        assert np.array_equal(mx1, mean[1]) and np.array_equal(mx1_ci, host['max_cluster_size_ci'],
+                                                               equal_nan=True)
+        ctx.reset_accumulators()
+        ctx.close()
+
+
 def test_study_driver_equals_jugfile_pipeline(tmp_path):
     """finite_size_study == the jugfile's task graph (percolate/share/jugfile.py:166-259):
     same seeds recipe, reduce(bond_reduce, map(bond_run, seeds)), finalize -- checked
