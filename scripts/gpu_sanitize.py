@@ -21,6 +21,7 @@ for g, runs in ((lowering.lowered_spanning_2d_grid(24), 40), (lowering.lowered_s
             ctx.reset_accumulators()
             ctx.run_fused(runs, mode, seeds, _native.FUSE_MICRO | _native.FUSE_CANON)
             ctx.micro_finalize()
+            ctx.micro_arrays(-1.0, 1.0, norm=g.num_nodes)
             ctx.canon_export()
         ctx.run_rows(min(runs, 3), _native.PERM_FEISTEL, seeds[:3])
         ctx.close()

@@ -689,6 +689,10 @@ def test_missing_graph_and_bad_arguments_fail_loudly():
     with pytest.raises(n.NativeError):
         ctx.micro_finalize()                                                                # no runs
     with pytest.raises(n.NativeError):
+        ctx.micro_arrays(-1.0, 1.0)                                                         # no runs
+    with pytest.raises(n.NativeError):
+        ctx.micro_arrays(-1.0, 1.0, norm=0.0)                                               # bad divisor
+    with pytest.raises(n.NativeError):
         ctx.set_ps(np.array([1.5]))
     ctx.close()
 
