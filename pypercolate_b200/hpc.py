@@ -505,21 +505,10 @@ def bond_statistics_batch(
 
     runs = ctx.micro_runs
     # means, Student-t intervals and the per-site normalisation are evaluated on the
-    # device (pz_micro_arrays: the host formulas, operation for operation); the two
-    # t quantiles depend on (alpha, runs) only
-    with np.errstate(invalid='ignore'):
-        t_lo, t_hi = scipy.stats.t.interval(1 - alpha, df=runs - 1)
-    k, largest, largest_ci, moments, moments_ci = ctx.micro_arrays(
-        t_lo, t_hi, norm=lowered.num_nodes)
-    arrays = {
-        'max_cluster_size': largest, 'max_cluster_size_ci': largest_ci,
-        'moments': moments, 'moments_ci': moments_ci,
-    }
-    if spanning_cluster:
-        arrays['spanning_cluster'] = (k + 1) / (runs + 2)
-        arrays['spanning_cluster_ci'] = _percolate._beta_interval_rows(k, runs, alpha)
-    arrays['M'] = lowered.num_edges
-    arrays['N'] = lowered.num_nodes
+    # device (pz_micro_arrays: the host formulas, operation for operation)
+    arrays = _percolate._arrays_on_device(ctx, runs, alpha, lowered.num_nodes,
+                                          lowered.num_edges, spanning_cluster,
+                                          norm=lowered.num_nodes)
     count, cmean, cm2 = ctx.canon_export()
     averages = _canonical_averages_from_partials(count, cmean, cm2, spanning_cluster)
     finalized = finalize_canonical_averages(lowered.num_nodes, ps, averages, alpha)

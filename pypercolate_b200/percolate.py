@@ -377,11 +377,9 @@ class _MicrocanonicalAverages(object):
         ctx = _context(g)
         ctx.reset_accumulators()
         ctx.run_fused(runs, _native.PERM_HOST, perms, _native.FUSE_MICRO)
-        mean, var = ctx.micro_finalize()
+        self._arrays = _arrays_on_device(ctx, runs, alpha, g.num_nodes,
+                                         g.num_edges, self._spanning)
         ctx.reset_accumulators()
-        self._arrays = _arrays_from_device(mean, var, runs, alpha,
-                                           g.num_nodes, g.num_edges,
-                                           self._spanning)
 
     def raw_arrays(self):
         """Un-normalised per-n arrays (used by microcanonical_averages_arrays
@@ -436,8 +434,29 @@ class _MicrocanonicalAverages(object):
     next = __next__
 
 
+def _arrays_on_device(ctx, runs, alpha, num_nodes, num_edges, spanning, norm=1.0):
+    """Per-n statistics of the runs folded into ``ctx``, each divided by ``norm``: the
+    formulas of ``_arrays_from_device`` evaluated by ``pz_micro_arrays`` on the GPU
+    (operation for operation, hence bit-identical); only the two Student-t quantiles,
+    which depend on ``(alpha, runs)`` alone, and the beta table look-up stay on the host."""
+    with np.errstate(invalid='ignore'):
+        t_lo, t_hi = scipy.stats.t.interval(1 - alpha, df=runs - 1)
+    k, largest, largest_ci, moments, moments_ci = ctx.micro_arrays(t_lo, t_hi, norm=norm)
+    ret = {
+        'max_cluster_size': largest, 'max_cluster_size_ci': largest_ci,
+        'moments': moments, 'moments_ci': moments_ci,
+    }
+    if spanning:
+        ret['spanning_cluster'] = (k + 1) / (runs + 2)
+        ret['spanning_cluster_ci'] = _beta_interval_rows(k, runs, alpha)
+    ret['M'] = num_edges
+    ret['N'] = num_nodes
+    return ret
+
+
 def _arrays_from_device(mean, var, runs, alpha, num_nodes, num_edges, spanning):
-    """Per-n statistics (NOT yet divided by N) from the device reduction."""
+    """Per-n statistics (NOT yet divided by N) from the device means / variances: the host
+    form of ``_arrays_on_device`` (kept as its specification; the parity tests compare the two)."""
     ret = dict()
     ret['max_cluster_size'] = mean[1]
     ret['max_cluster_size_ci'] = _interval(mean[1], var[0], runs, alpha)
