@@ -730,6 +730,35 @@ struct StoreS16BF : StoreS16B {
         if (m != (((sa >= sb ? ta : tb) >> 17) & 3u)) flag[big] = (uint8_t)(1u | (m << 1));
         return m;
     }
+    // K walks of find_rep at once: the dependent shared-memory loads of the K chains are issued
+    // back to back, so a step costs one load latency for all of them instead of K
+    template <int K>
+    __device__ __forceinline__ void find_rep_multi(uint32_t (&x)[K]) {
+        uint32_t f[K];
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < K; ++k) { f[k] = flag_acquire(x[k]); any |= !(f[k] & 1u); }
+        while (any) {
+            uint32_t p[K], fp[K], g[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) p[k] = (f[k] & 1u) ? x[k] : (uint32_t)val[x[k]];   // parent (flag was clear)
+#pragma unroll
+            for (int k = 0; k < K; ++k) fp[k] = (f[k] & 1u) ? 1u : flag_acquire(p[k]);
+#pragma unroll
+            for (int k = 0; k < K; ++k) g[k] = (fp[k] & 1u) ? p[k] : (uint32_t)val[p[k]];  // grandparent
+            any = false;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if (!(f[k] & 1u)) {
+                    if (fp[k] & 1u) { x[k] = p[k]; f[k] = 1u; }          // the parent is a root: done
+                    else { val[x[k]] = (uint16_t)g[k]; x[k] = g[k]; f[k] = 0u; }   // halve, go on from g
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                if (!(f[k] & 1u)) { f[k] = flag_acquire(x[k]); any |= !(f[k] & 1u); }
+        }
+    }
     // finder: walk x up while merges may be in flight; returns an ancestor-or-self of x that
     // was a root when its flag was read (path halving on the way)
     __device__ __forceinline__ uint32_t find_rep(uint32_t x) {
@@ -749,6 +778,10 @@ struct StoreS16BF : StoreS16B {
 
 // (launch bound = the CTA plus one 256-thread CTA of the bond-order kernel: that caps the registers
 // at 72 per thread, so that perm_feistel_kernel of the next chunk still finds room on the SM)
+// 1: a finder thread walks the two endpoints of a bond up the forest together
+#ifndef PZ_FIND_ILP
+#define PZ_FIND_ILP 1
+#endif
 #ifndef PZ_TAIL_MAX
 #define PZ_TAIL_MAX 32                        // pending bonds at or below which warp 0 finishes the batch
 #endif
@@ -825,8 +858,14 @@ __global__ void __launch_bounds__(FW_ALL + 256, 1) sweep_fw_kernel(SweepArgs a, 
                     uint32_t u = 0, v = 0;
                     if (n < M) {
                         edge_uv(uv, u, v);
+#if PZ_FIND_ILP
+                        uint32_t x[2] = {u, v};
+                        st.template find_rep_multi<2>(x);
+                        u = x[0]; v = x[1];
+#else
                         u = st.find_rep(u);
                         v = st.find_rep(v);
+#endif
                     }
                     out[q] = u | (v << 16);
                 }
