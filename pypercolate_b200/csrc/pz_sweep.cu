@@ -621,8 +621,9 @@ __global__ void __launch_bounds__(32 * CTA_WARPS, 1) sweep_cta_kernel(SweepArgs 
                             const uint32_t add = (((total >> 40) & 0x3ffu) ? 1u : 0u) |
                                                  (((total >> 50) & 0x3ffu) ? 2u : 0u);
                             st.set_root(hub, hub_m1 + tot_sz, track ? add : 0u);
-                            atomicMax(&sh->hub_key,
-                                      ((unsigned long long)(hub_m1 + tot_sz + 1) << 32) | hub);
+                            // the star phase has one writer of the hub: plain compare and store, no CAS loop
+                            const unsigned long long nk = ((unsigned long long)(hub_m1 + tot_sz + 1) << 32) | hub;
+                            if (nk > sh->hub_key) sh->hub_key = nk;
                         }
                         won = true;
                     }
@@ -1002,8 +1003,9 @@ __global__ void __launch_bounds__(FW_ALL + 256, 1) sweep_fw_kernel(SweepArgs a, 
                                             const uint32_t add = (((total >> 40) & 0x3ffu) ? 1u : 0u) |
                                                                  (((total >> 50) & 0x3ffu) ? 2u : 0u);
                                             st.set_root(hub, hub_m1 + tot_sz, track ? add : 0u);
-                                            atomicMax(&sh->hub_key,
-                                                      ((unsigned long long)(hub_m1 + tot_sz + 1) << 32) | hub);
+                                            // the star phase has one writer of the hub: plain compare and store, no CAS loop
+                                            const unsigned long long nk = ((unsigned long long)(hub_m1 + tot_sz + 1) << 32) | hub;
+                                            if (nk > sh->hub_key) sh->hub_key = nk;
                                         }
                                         xp = false;
                                     }
@@ -1113,8 +1115,9 @@ __global__ void __launch_bounds__(FW_ALL + 256, 1) sweep_fw_kernel(SweepArgs a, 
                                 const uint32_t add = (((total >> 40) & 0x3ffu) ? 1u : 0u) |
                                                      (((total >> 50) & 0x3ffu) ? 2u : 0u);
                                 st.set_root(hub, hub_m1 + tot_sz, track ? add : 0u);
-                                atomicMax(&sh->hub_key,
-                                          ((unsigned long long)(hub_m1 + tot_sz + 1) << 32) | hub);
+                                // the star phase has one writer of the hub: plain compare and store, no CAS loop
+                                const unsigned long long nk = ((unsigned long long)(hub_m1 + tot_sz + 1) << 32) | hub;
+                                if (nk > sh->hub_key) sh->hub_key = nk;
                             }
                             won = true;
                         }
