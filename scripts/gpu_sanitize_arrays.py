@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from pypercolate_b200 import _native, lowering
 
-for g in (lowering.lowered_spanning_2d_grid(24), lowering.lowered_spanning_3d_grid(5)):
+for g in (lowering.lowered_spanning_2d_grid(24), lowering.lowered_spanning_1d_chain(10)):     # M + 1 = 1105, 10
     ctx = _native.Context(0)
     ctx.set_graph(g)
     seeds = np.arange(40, dtype=np.uint32) + 3

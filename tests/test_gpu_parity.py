@@ -463,8 +463,9 @@ def test_device_micro_arrays_equal_host_evaluation():
     import scipy.stats
     from pypercolate_b200 import lowering, percolate
     n = _native()
-    for L, runs, alpha in ((8, 70, 0.05), (32, 40, percolate.alpha_1sigma), (5, 1, 0.3)):
-        g = lowering.lowered_spanning_2d_grid(L)
+    for L, runs, alpha in ((8, 70, 0.05), (32, 40, percolate.alpha_1sigma), (5, 1, 0.3), (-10, 30, 0.1)):
+        # (2D grids have an odd number of rows M + 1; the chain of 10 has an even one)
+        g = lowering.lowered_spanning_2d_grid(L) if L > 0 else lowering.lowered_spanning_1d_chain(-L)
         ctx = ctx_for(g)
         ctx.reset_accumulators()
         ctx.run_fused(runs, n.PERM_MT19937, np.arange(runs, dtype=np.uint32) + 17, n.FUSE_MICRO)
