@@ -3,6 +3,7 @@
 // expand_rows      records -> packed microcanonical_statistics_dtype rows
 //                  (percolate/hpc.py:57-70; the per-bond bookkeeping of
 //                  hpc.py:249-307 re-expressed as a block-wide prefix scan)
+#include <cstdlib>
 #include "pz_common.cuh"
 #include "pz_internal.h"
 
@@ -242,10 +243,100 @@ __global__ void __launch_bounds__(ROWS_THREADS) checkpoint_kernel(StatsArgs a, R
     }
 }
 
+// The same checkpoints with ONE WARP PER RUN: a lane takes 8 consecutive records (two 16-byte loads
+// when the rows of the record array are aligned), the warp scans 256 records per step and carries
+// the running state in registers -- no shared memory, no CTA barriers, no cross-warp prefix.  A
+// batch has thousands of runs, so a warp per run still fills the GPU.  The state after row k (the
+// records before k applied) is the exclusive prefix of the lane that starts at record k.
+__device__ __forceinline__ Delta delta_shfl(const Delta &d, int src) {
+    Delta r;
+    r.c = __shfl_sync(0xffffffffu, d.c, src);
+    r.mx = __shfl_sync(0xffffffffu, d.mx, src);
+    r.s2 = __shfl_sync(0xffffffffu, d.s2, src);
+    r.s3 = __shfl_sync(0xffffffffu, d.s3, src);
+    r.s4 = __shfl_sync(0xffffffffu, d.s4, src);
+    return r;
+}
+
+template <class RecT>
+__device__ __forceinline__ void load8_records(const RecT *recs, int M, int k0, bool vec, RecT (&r)[CK_ITEMS])
+{
+    if constexpr (sizeof(RecT) == 4) {
+        if (vec && k0 + CK_ITEMS <= M) {
+            const uint4 *p = reinterpret_cast<const uint4 *>(recs + k0);
+            const uint4 x = __ldg(p), y = __ldg(p + 1);
+            r[0] = x.x; r[1] = x.y; r[2] = x.z; r[3] = x.w;
+            r[4] = y.x; r[5] = y.y; r[6] = y.z; r[7] = y.w;
+            return;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < CK_ITEMS; ++i) r[i] = (k0 + i < M) ? __ldg(&recs[k0 + i]) : (RecT)0;
+}
+
+template <class RecT>
+__global__ void __launch_bounds__(128) checkpoint_warp_kernel(StatsArgs a, RunState *ckpt, int every,
+                                                              int n_ckpt)
+{
+    static_assert(CK_ITEMS == 8, "a lane takes 8 records");
+    const int lane = threadIdx.x & 31;
+    const int run = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (run >= a.R) return;                                   // the whole warp leaves
+    const int M = a.M;
+    const RecT *recs = reinterpret_cast<const RecT *>(a.recs) + (size_t)run * M;
+    RunState *out = ckpt + (size_t)run * n_ckpt;
+    const bool vec = sizeof(RecT) == 4 && (M & 3) == 0;      // every run's records start 16-byte aligned
+    constexpr int STEP = 32 * CK_ITEMS;
+    Delta carry{0u, 1u, (uint64_t)a.N, (uint64_t)a.N, (uint64_t)a.N};      // the state at row 0
+    RecT nxt[CK_ITEMS];
+    load8_records<RecT>(recs, M, CK_ITEMS * lane, vec, nxt);
+    for (int base = 0; base <= M; base += STEP) {
+        const int k0 = base + CK_ITEMS * lane;                // this lane: records k0 .. k0+7
+        RecT r[CK_ITEMS];
+#pragma unroll
+        for (int i = 0; i < CK_ITEMS; ++i) r[i] = nxt[i];
+        if (base + STEP <= M) load8_records<RecT>(recs, M, k0 + STEP, vec, nxt);   // the next step's records
+        Delta d = delta_of<RecT>(r[0]);
+#pragma unroll
+        for (int i = 1; i < CK_ITEMS; ++i) d = delta_combine(d, delta_of<RecT>(r[i]));
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) {
+            const Delta o = delta_shfl_up(d, k);
+            if (lane >= k) d = delta_combine(o, d);
+        }
+        Delta excl = delta_shfl_up(d, 1);
+        if (lane == 0) excl = Delta{0, 0, 0, 0, 0};
+        if (k0 <= M && (k0 % every) == 0) {
+            const Delta pre = delta_combine(carry, excl);     // state after row k0
+            RunState st;
+            st.c = pre.c; st.mx = pre.mx; st.s2 = pre.s2; st.s3 = pre.s3; st.s4 = pre.s4;
+            out[k0 / every] = st;
+        }
+        carry = delta_combine(carry, delta_shfl(d, 31));
+    }
+}
+
+// PZ_CKPT_WARP=0: the block-scan kernel (one CTA per run)
+static int ckpt_warp_mode()
+{
+    static int mode = -1;
+    if (mode < 0) {
+        const char *e = getenv("PZ_CKPT_WARP");
+        mode = e ? (atoi(e) != 0) : 1;
+    }
+    return mode;
+}
+
 cudaError_t launch_checkpoints(const StatsArgs &a, RunState *ckpt, int every, int n_ckpt,
                                cudaStream_t s)
 {
     if (a.R <= 0) return cudaSuccess;
+    if (ckpt_warp_mode() && every % CK_ITEMS == 0) {
+        const int grid = (a.R + 3) / 4;
+        if (a.rec64) checkpoint_warp_kernel<uint64_t><<<grid, 128, 0, s>>>(a, ckpt, every, n_ckpt);
+        else checkpoint_warp_kernel<uint32_t><<<grid, 128, 0, s>>>(a, ckpt, every, n_ckpt);
+        return cudaGetLastError();
+    }
     if (a.rec64) checkpoint_kernel<uint64_t><<<a.R, ROWS_THREADS, 0, s>>>(a, ckpt, every, n_ckpt);
     else checkpoint_kernel<uint32_t><<<a.R, ROWS_THREADS, 0, s>>>(a, ckpt, every, n_ckpt);
     return cudaGetLastError();
