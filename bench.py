@@ -163,7 +163,9 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference is pure Python (~4e4 bond-additions/s per core, BASELINE.md) and "
                 "cannot travel to the GPU box; this arm times the C restatement of its algorithm "
-                "(oracle/pz_oracle.c) on all host cores",
+                "(oracle/pz_oracle.c) on all host cores.  It materialises the rows of every run "
+                "(bond_microcanonical_statistics) but does NOT average them or contract them with the "
+                "binomial weights, i.e. it does less work per run than the GPU arm",
     }
     emit(line)
 
