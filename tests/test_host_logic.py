@@ -202,3 +202,141 @@ def test_study_seed_recipe_and_disk_format(tmp_path):
     study.write_to_disk(path, 32, b)
     with np.load(path) as z:
         assert z['32'].dtype == b.dtype and np.array_equal(z['32'], b)
+
+
+# ---------------------------------------------------------------------------
+# per-n averaging helpers (percolate/percolate.py:450-705, 968-1064)
+# ---------------------------------------------------------------------------
+def _random_runs(rng, runs, rows, constant_rows=()):
+    """Integer per-run statistics [rows, runs] like the sweep produces; some rows identical in every run."""
+    largest = rng.integers(1, 5000, size=(rows, runs)).astype(np.float64)
+    moments = rng.integers(0, 2 ** 40, size=(rows, runs, 5)).astype(np.float64)
+    spans = rng.random((rows, runs)) < np.linspace(0, 1, rows)[:, None]
+    for n in constant_rows:
+        largest[n] = largest[n, 0]
+        moments[n] = moments[n, 0]
+    return largest, moments, spans
+
+
+def test_per_n_helpers_formulas():
+    rng = np.random.default_rng(5)
+    runs, alpha = 23, 0.1
+    largest, moments, spans = _random_runs(rng, runs, 4, constant_rows=(2,))
+    for n in range(4):
+        got = percolate._microcanonical_average_max_cluster_size(largest[n], alpha)
+        mean, std = largest[n].mean(), largest[n].std(ddof=1)
+        assert got['max_cluster_size'] == mean
+        if n == 2:                                   # percolate/percolate.py:621-633: zero spread -> (mean, mean)
+            assert std == 0 and np.array_equal(got['max_cluster_size_ci'], [mean, mean])
+        else:
+            want = scipy.stats.t.interval(1 - alpha, df=runs - 1, loc=mean, scale=std / np.sqrt(runs))
+            assert np.array_equal(got['max_cluster_size_ci'], want)
+        gm = percolate._microcanonical_average_moments(moments[n], alpha)
+        assert np.array_equal(gm['moments'], moments[n].mean(axis=0)) and gm['moments_ci'].shape == (5, 2)
+        if n == 2:
+            assert np.array_equal(gm['moments_ci'][:, 0], gm['moments']) and \
+                np.array_equal(gm['moments_ci'][:, 1], gm['moments'])
+        gs = percolate._microcanonical_average_spanning_cluster(spans[n], alpha)
+        k = spans[n].sum()
+        assert gs['spanning_cluster'] == (k + 1) / (runs + 2)
+        assert np.array_equal(gs['spanning_cluster_ci'],
+                              scipy.stats.beta.ppf([alpha / 2, 1 - alpha / 2], k + 1, runs - k + 1))
+
+
+def test_vectorised_arrays_equal_the_per_n_helpers():
+    """_arrays_from_device (the host specification of pz_micro_arrays) against the per-n functions the
+    reference calls once per bond count; means and unbiased variances formed like the device does."""
+    rng = np.random.default_rng(11)
+    runs, rows, alpha = 40, 60, percolate.alpha_1sigma
+    largest, moments, spans = _random_runs(rng, runs, rows, constant_rows=(0, 7, rows - 1))
+    mean = np.empty((7, rows)); var = np.empty((6, rows))
+    mean[0] = spans.sum(axis=1)
+    mean[1] = largest.mean(axis=1); var[0] = largest.var(axis=1, ddof=1)
+    mean[2:7] = moments.mean(axis=1).T; var[1:6] = moments.var(axis=1, ddof=1).T
+    got = percolate._arrays_from_device(mean, var, runs, alpha, 1000, rows - 1, True)
+    for n in range(rows):
+        a = percolate._microcanonical_average_max_cluster_size(largest[n], alpha)
+        b = percolate._microcanonical_average_moments(moments[n], alpha)
+        c = percolate._microcanonical_average_spanning_cluster(spans[n], alpha)
+        np.testing.assert_allclose(got['max_cluster_size'][n], a['max_cluster_size'], rtol=1e-13)
+        np.testing.assert_allclose(got['max_cluster_size_ci'][n], a['max_cluster_size_ci'], rtol=1e-12)
+        np.testing.assert_allclose(got['moments'][:, n], b['moments'], rtol=1e-13)
+        np.testing.assert_allclose(got['moments_ci'][:, n], b['moments_ci'], rtol=1e-12)
+        assert got['spanning_cluster'][n] == c['spanning_cluster']
+        np.testing.assert_allclose(got['spanning_cluster_ci'][n], c['spanning_cluster_ci'], rtol=1e-12)
+    for n in (0, 7, rows - 1):                       # identical runs: the interval collapses exactly
+        assert np.array_equal(got['max_cluster_size_ci'][n], [got['max_cluster_size'][n]] * 2)
+
+
+def _per_n_dicts(rng, rows, spanning):
+    out = []
+    for n in range(rows):
+        d = {'n': n, 'N': 50, 'M': rows - 1, 'max_cluster_size': rng.random() * 50,
+             'max_cluster_size_ci': rng.random(2) * 50, 'moments': rng.random(5) * 1e6,
+             'moments_ci': rng.random((5, 2)) * 1e6}
+        if spanning:
+            d['spanning_cluster'] = rng.random()
+            d['spanning_cluster_ci'] = rng.random(2)
+        out.append(d)
+    return out
+
+
+@pytest.mark.parametrize("spanning", [True, False])
+def test_microcanonical_averages_arrays_from_any_iterable(spanning):
+    """The generic path (an iterable of per-n dictionaries, percolate/percolate.py:1022-1064): stacking,
+    the (5, M+1[, 2]) layout of the moments and the division by N of everything but the spanning keys."""
+    dicts = _per_n_dicts(np.random.default_rng(3), 9, spanning)
+    got = percolate.microcanonical_averages_arrays(iter(dicts))
+    assert got['M'] == 8 and got['N'] == 50
+    assert ('spanning_cluster' in got) == spanning
+    for n, d in enumerate(dicts):
+        assert got['max_cluster_size'][n] == d['max_cluster_size'] / 50
+        assert np.array_equal(got['max_cluster_size_ci'][n], d['max_cluster_size_ci'] / 50)
+        assert np.array_equal(got['moments'][:, n], d['moments'] / 50)
+        assert np.array_equal(got['moments_ci'][:, n], d['moments_ci'] / 50)
+        if spanning:
+            assert got['spanning_cluster'][n] == d['spanning_cluster']
+            assert np.array_equal(got['spanning_cluster_ci'][n], d['spanning_cluster_ci'])
+    assert got['moments'].shape == (5, 9) and got['moments_ci'].shape == (5, 9, 2)
+
+
+def test_host_helpers_against_the_live_reference():
+    """Same inputs through the unmodified reference's helpers (build container only)."""
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not present")
+    ref, _ = ref_shim.load()
+    rng = np.random.default_rng(17)
+    largest, moments, spans = _random_runs(rng, 12, 3, constant_rows=(1,))
+    for n in range(3):
+        for ours, theirs, arg in (
+                (percolate._microcanonical_average_max_cluster_size,
+                 ref._microcanonical_average_max_cluster_size, largest[n]),
+                (percolate._microcanonical_average_moments, ref._microcanonical_average_moments, moments[n]),
+                (percolate._microcanonical_average_spanning_cluster,
+                 ref._microcanonical_average_spanning_cluster, spans[n])):
+            a, b = ours(arg, 0.2), theirs(arg, 0.2)
+            assert a.keys() == b.keys()
+            for key in a:
+                assert np.array_equal(np.asarray(a[key]), np.asarray(b[key])), key
+    for spanning in (True, False):
+        dicts = _per_n_dicts(np.random.default_rng(4), 6, spanning)
+        a = percolate.microcanonical_averages_arrays(iter(dicts))
+        b = ref.microcanonical_averages_arrays(iter(dicts))
+        assert a.keys() == b.keys()
+        for key in a:
+            assert np.array_equal(np.asarray(a[key]), np.asarray(b[key])), key
+    for L in (1, 2, 4):
+        for ours, theirs in ((percolate.spanning_2d_grid, ref.spanning_2d_grid),
+                             (percolate.spanning_1d_chain, ref.spanning_1d_chain)):
+            a, b = ours(L), theirs(L)
+            assert list(a.nodes(data=True)) == list(b.nodes(data=True))
+            assert list(a.edges(data=True)) == list(b.edges(data=True))
+            pa, pb = percolate.percolation_graph(a), ref.percolation_graph(b)
+            assert pa.keys() == pb.keys()
+            for key in pa:
+                if key in ('graph', 'perc_graph'):
+                    assert list(pa[key].edges()) == list(pb[key].edges())
+                    assert list(pa[key].nodes()) == list(pb[key].nodes())
+                else:
+                    assert pa[key] == pb[key], key
