@@ -1,3 +1,7 @@
+// Round-count simulator of the lock-step sweep (host C, exact claims, no hash collisions): batches of 512 bonds,
+// earliest-bond-wins claim rounds, star merging into the K largest clusters, tail mode.
+//   gcc -O2 -o sim scripts/sim_rounds.c;  ./sim L policy K tailmax [seed]      (policy 0: one hub; 1: K hubs, THR=<min size> env)
+// Reproduces 825 rounds / 213 tails per L=256 run (831 / 215 measured in the kernel).  See profiles/sweep_cta_shape_r1.txt.
 // round-count simulator of the lock-step sweep (exact claims, no hash collisions)
 #include <stdio.h>
 #include <stdlib.h>

@@ -1,3 +1,5 @@
+// Variant of sim_rounds.c: the <= carrymax pending bonds of a batch are carried into the next batch as its earliest bonds.
+//   gcc -O2 -o sim2 scripts/sim_rounds_carry.c;  ./sim2 L carrymax tailmax [seed]
 // carry-over simulator: pending bonds (<= CARRY) of a batch are carried into the next batch as its earliest elements
 #include <stdio.h>
 #include <stdlib.h>

@@ -1,3 +1,6 @@
+// Carried-over bonds AND K hubs (env K, THR), with a check of every merge record against the sequential run.
+//   gcc -O2 -o sim4 scripts/sim_rounds_hubs_carry.c;  K=2 THR=256 ./sim4 L carrymax tailmax [seed]
+// This is the executable specification of the sweep design proposed for the next round.
 // carry-over simulator: pending bonds (<= CARRY) of a batch are carried into the next batch as its earliest elements
 #include <stdio.h>
 #include <stdlib.h>
