@@ -40,9 +40,14 @@ enum pz_perm_mode {
     PZ_PERM_MT19937 = 2,   /* uint32 seeds[R]; numpy RandomState(seed).permutation(M)
                               reproduced on the device bit for bit                      */
     PZ_PERM_PHILOX = 3,    /* uint32 seeds[R]; Philox4x32-10 bucketed Fisher-Yates       */
-    PZ_PERM_FEISTEL = 4    /* uint32 seeds[R]; Philox-keyed 20-round Feistel bijection of
+    PZ_PERM_FEISTEL = 4,   /* uint32 seeds[R]; Philox-keyed 20-round Feistel bijection of
                               [0, M) with cycle walking: order[n] = pi_seed(n), no
-                              scratch and no shared memory (the throughput mode)        */
+                              scratch and no shared memory                              */
+    PZ_PERM_PHILOX_FY = 5  /* uint32 seeds[R]; textbook Fisher-Yates (i = M-1..1, swap with
+                              j in [0, i]) with unbiased Lemire draws from Philox4x32-10
+                              counters: one thread per run, no shared memory; like
+                              PZ_PERM_MT19937 it is generated underneath the sweep of the
+                              previous batch of runs                                    */
 };
 
 /* OR into a device-RNG perm_mode when the seeds already live in device memory */
@@ -94,7 +99,7 @@ int pz_run_rows(pz_ctx *ctx, int32_t R, int perm_mode, const void *perm_src,
 
 /*
  * Bond orders only: the device replacement of RandomState(seed).permutation(M)
- * (percolate/hpc.py:195,206).  perm_mode is PZ_PERM_MT19937, PZ_PERM_PHILOX or PZ_PERM_FEISTEL;
+ * (percolate/hpc.py:195,206).  perm_mode is any of the device RNG modes (PZ_PERM_MT19937 ..);
  * seeds host uint32[R]; out int32[R][M] (host, or device when is_device != 0).
  */
 int pz_make_perms(pz_ctx *ctx, int32_t R, int perm_mode, const uint32_t *seeds,
@@ -203,9 +208,32 @@ int pz_canon_merge(pz_ctx *ctx, int64_t count, const double *mean, const double 
 /* forget the canonical partials only (the micro accumulators are kept) */
 int pz_canon_reset(pz_ctx *ctx);
 
-/* per-run canonical statistics of the LAST pz_run_fused(PZ_FUSE_CANON) call:
- * host double[R][num_p][PZ_CANON_COLS] (parity tests, small R) */
+/* per-run canonical statistics of the LAST batch of runs the last pz_run_fused(PZ_FUSE_CANON)
+ * call put through the device (a call is cut into batches by scratch memory; a call that fits
+ * one batch -- parity tests, small R -- is covered whole): pz_canon_last_count() runs,
+ * host double[count][num_p][PZ_CANON_COLS] */
+int32_t pz_canon_last_count(const pz_ctx *ctx);
 int pz_canon_last_runs(pz_ctx *ctx, double *out);
+
+/*
+ * Cross-GPU exchange: one process per GPU, NCCL over NVLink / NVSwitch (loaded at run time;
+ * nothing here is needed on one GPU).  Replaces the reduction of the per-task results of a
+ * study, bond_reduce over pickles on a shared file system (percolate/share/jugfile.py:126-135,
+ * 240-244).  Rank 0 obtains an id with pz_comm_unique_id and hands its PZ_COMM_ID_BYTES bytes
+ * to the other ranks by any means (a shared file, MPI, sockets); every rank then calls
+ * pz_comm_init (collective).  pz_allreduce (collective) combines the accumulators of all
+ * ranks' contexts in ONE step on the context's stream: the micro accumulators and the run
+ * count by a word-wise integer all-reduce (exact: 32-bit limbs in 64-bit words), the canonical
+ * partials by an all-gather and a Chan merge in rank order (bit-identical on every rank).
+ * Afterwards every rank holds the totals.
+ */
+#define PZ_COMM_ID_BYTES 128
+int pz_comm_unique_id(void *id_out);
+int pz_comm_init(pz_ctx *ctx, int world, int rank, const void *id);
+int pz_comm_destroy(pz_ctx *ctx);
+int pz_comm_world(const pz_ctx *ctx);
+int pz_comm_rank(const pz_ctx *ctx);
+int pz_allreduce(pz_ctx *ctx);
 
 /*
  * Per-phase device time, measured with CUDA events on the context's stream

@@ -17,9 +17,10 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PZ_B200_LIB") or os.path.join(_HERE, "libpz_b200.so")   # env: A/B builds
 
-PERM_HOST, PERM_DEVICE, PERM_MT19937, PERM_PHILOX, PERM_FEISTEL = 0, 1, 2, 3, 4
+PERM_HOST, PERM_DEVICE, PERM_MT19937, PERM_PHILOX, PERM_FEISTEL, PERM_PHILOX_FY = 0, 1, 2, 3, 4, 5
 # rng keyword of the Python API -> perm_mode
-RNG_MODES = {'mt19937': PERM_MT19937, 'philox': PERM_PHILOX, 'feistel': PERM_FEISTEL}
+RNG_MODES = {'mt19937': PERM_MT19937, 'philox': PERM_PHILOX, 'feistel': PERM_FEISTEL,
+             'philox_fy': PERM_PHILOX_FY}
 FUSE_MICRO, FUSE_CANON = 1, 2
 SEEDS_ON_DEVICE = 0x100
 ACC_WORDS = 25
@@ -32,9 +33,11 @@ SYMBOLS = [
     "pz_run_rows", "pz_run_fused", "pz_reset_accumulators", "pz_micro_runs",
     "pz_micro_export", "pz_micro_import", "pz_micro_finalize", "pz_micro_arrays", "pz_set_ps",
     "pz_convolve", "pz_canonical_statistics_rows", "pz_canon_export",
-    "pz_canon_merge", "pz_canon_last_runs", "pz_launch_count",
+    "pz_canon_merge", "pz_canon_last_runs", "pz_canon_last_count", "pz_launch_count",
     "pz_make_perms", "pz_profile", "pz_profile_read", "pz_canon_reset", "pz_timer_start", "pz_timer_stop",
+    "pz_comm_unique_id", "pz_comm_init", "pz_comm_destroy", "pz_comm_world", "pz_comm_rank", "pz_allreduce",
 ]
+COMM_ID_BYTES = 128
 
 
 class NativeError(RuntimeError):
@@ -91,11 +94,19 @@ def load():
         L.pz_canon_export.argtypes = [vp, ctypes.POINTER(i64), vp, vp]
         L.pz_canon_merge.argtypes = [vp, i64, vp, vp]
         L.pz_canon_last_runs.argtypes = [vp, vp]
+        L.pz_canon_last_count.argtypes = [vp]
+        L.pz_canon_last_count.restype = i32
         L.pz_canon_reset.argtypes = [vp]
         L.pz_timer_start.argtypes = [vp]
         L.pz_timer_stop.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
         L.pz_launch_count.argtypes = [vp]
         L.pz_launch_count.restype = i64
+        L.pz_comm_unique_id.argtypes = [vp]
+        L.pz_comm_init.argtypes = [vp, ci, ci, vp]
+        L.pz_comm_destroy.argtypes = [vp]
+        L.pz_comm_world.argtypes = [vp]
+        L.pz_comm_rank.argtypes = [vp]
+        L.pz_allreduce.argtypes = [vp]
         _lib = L
         return _lib
 
@@ -300,9 +311,32 @@ class Context(object):
             self.canon_merge(count, mean, m2)
 
     def canon_last_runs(self, R):
+        last = int(self._L.pz_canon_last_count(self._h))
+        if last != R:
+            raise NativeError("canon_last_runs: the last device batch held %d runs, not %d" % (last, R))
         out = np.empty((R, self.num_p, CANON_COLS), dtype=np.float64)
         _check(self._L.pz_canon_last_runs(self._h, _ptr(out)))
         return out
+
+    # -- cross-GPU exchange (NCCL through the C-ABI) -----------------------------
+    def comm_init(self, world, rank, comm_id):
+        """Join the communicator identified by ``comm_id`` (``comm_unique_id()`` of rank 0,
+        ``COMM_ID_BYTES`` bytes).  Collective over the ``world`` ranks."""
+        buf = bytes(comm_id)
+        if len(buf) != COMM_ID_BYTES:
+            raise ValueError("comm_id must be %d bytes" % COMM_ID_BYTES)
+        _check(self._L.pz_comm_init(self._h, int(world), int(rank), ctypes.c_char_p(buf)))
+
+    def comm_destroy(self):
+        _check(self._L.pz_comm_destroy(self._h))
+
+    @property
+    def comm_world(self):
+        return int(self._L.pz_comm_world(self._h))
+
+    def allreduce(self):
+        """Combine the accumulators of every rank's context (collective)."""
+        _check(self._L.pz_allreduce(self._h))
 
     def timer_start(self):
         _check(self._L.pz_timer_start(self._h))
@@ -315,6 +349,13 @@ class Context(object):
     @property
     def launch_count(self):
         return int(self._L.pz_launch_count(self._h))
+
+
+def comm_unique_id():
+    """Fresh communicator id (rank 0 calls this and hands the bytes to the other ranks)."""
+    buf = ctypes.create_string_buffer(COMM_ID_BYTES)
+    _check(load().pz_comm_unique_id(buf))
+    return buf.raw
 
 
 # -- one context per (device, graph) ---------------------------------------------

@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <cmath>
 
 #include "../../include/pz.h"
 #include "pz_common.cuh"
@@ -110,8 +111,15 @@ struct pz_ctx {
     DevBuf<double> pmf;                   // [num_p][M+1], rows in ascending-p order
     DevBuf<int32_t> band_lo, band_hi, tband_lo, tband_hi, porder_dev, canon_flags;
     DevBuf<double> sf;                    // survival functions [num_p][M+1]
-    DevBuf<int32_t> perm_super;           // MT19937 mode: bond orders of a whole super-chunk of runs
-    DevBuf<uint32_t> seed_super;
+    // thread-per-run generators (MT19937, Philox Fisher-Yates): bond orders of a whole super-chunk of
+    // runs, double buffered -- super-chunk k+1 is generated on s_perm underneath the sweeps of k
+    DevBuf<int32_t> perm_super[2];
+    DevBuf<uint32_t> seed_super[2];
+    cudaEvent_t super_ready[2] = {nullptr, nullptr}, super_free[2] = {nullptr, nullptr};
+    DevBuf<uint32_t> validate_bits;       // caller-supplied orders: one bit per (run, bond) + flag word
+    int *validate_host = nullptr;         // pinned copy of the flag word
+    uint32_t epoch_start = 0x003fffffu;   // first claim epoch of a run (PZ_EPOCH_START: tests)
+    bool trusted_orders = false;          // orders generated by this library: no validation
     DevBuf<double> cols;                  // scratch of the contraction
     DevBuf<double> cols_out;
     const double *canon_last_ptr = nullptr;   // per-run values of the last chunk of the last fused call
@@ -120,6 +128,13 @@ struct pz_ctx {
     std::vector<double> canon_mean, canon_m2;
 
     int64_t launches = 0;
+
+    // cross-GPU exchange (NCCL, loaded at run time): see pz_comm_init / pz_allreduce
+    void *comm = nullptr;                 // ncclComm_t
+    int comm_world = 1, comm_rank = 0;
+    DevBuf<double> comm_send, comm_recv;  // canonical partials: [1 + 2 cols] and [world][1 + 2 cols]
+    double *comm_host = nullptr;          // pinned staging of both
+    size_t comm_host_cap = 0;
 
     cudaEvent_t timer_a = nullptr, timer_b = nullptr;
 
@@ -192,6 +207,22 @@ cudaError_t launch_perm_mt19937(int32_t M, int32_t R, const uint32_t *seeds, int
                                 cudaStream_t s, int *launches);
 cudaError_t launch_perm_feistel(int32_t M, int32_t R, const uint32_t *seeds, int32_t *perms,
                                 cudaStream_t s, int *launches);
+cudaError_t launch_perm_philox_fy(int32_t M, int32_t R, const uint32_t *seeds, int32_t *perms,
+                                  cudaStream_t s, int *launches);
+int perm_serial_capacity(int sms);
+cudaError_t launch_validate_orders(int32_t M, int32_t R, const int32_t *perms, uint32_t *bitmap,
+                                   int *flag, cudaStream_t s);
+}
+
+static cudaError_t launch_perm_mode(int perm_mode, int32_t M, int32_t R, const uint32_t *seeds,
+                                    int32_t *perms, cudaStream_t s, int *l)
+{
+    switch (perm_mode) {
+    case PZ_PERM_PHILOX: return launch_perm_philox(M, R, seeds, perms, s, l);
+    case PZ_PERM_FEISTEL: return launch_perm_feistel(M, R, seeds, perms, s, l);
+    case PZ_PERM_PHILOX_FY: return launch_perm_philox_fy(M, R, seeds, perms, s, l);
+    default: return launch_perm_mt19937(M, R, seeds, perms, s, l);
+    }
 }
 
 extern "C" {
@@ -227,6 +258,15 @@ int pz_create(int device, pz_ctx **out)
     if (const char *e = getenv("PZ_CLAIM_LOG2")) c->claim_cap = atoi(e);
     if (const char *e = getenv("PZ_CTA_WARPS")) c->cta_warps = atoi(e);
     if (const char *e = getenv("PZ_CKPT_EVERY")) c->ckpt_every = atoi(e) == 64 ? 64 : 1024;
+    if (const char *e = getenv("PZ_EPOCH_START")) {
+        const long v = atol(e);
+        c->epoch_start = (uint32_t)std::min<long>(0x003fffffL, std::max<long>(0x1280L, v));
+    }
+    for (int k = 0; k < 2; ++k) {
+        PZ_CUDA(cudaEventCreateWithFlags(&c->super_ready[k], cudaEventDisableTiming));
+        PZ_CUDA(cudaEventCreateWithFlags(&c->super_free[k], cudaEventDisableTiming));
+    }
+    PZ_CUDA(cudaMallocHost(&c->validate_host, sizeof(int)));
     {
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b > 0)
@@ -251,7 +291,16 @@ void pz_destroy(pz_ctx *c)
         if (sl.sweep_done) cudaEventDestroy(sl.sweep_done);
         if (sl.stats_done) cudaEventDestroy(sl.stats_done);
     }
-    c->perm_super.release(); c->seed_super.release();
+    for (int k = 0; k < 2; ++k) {
+        c->perm_super[k].release(); c->seed_super[k].release();
+        if (c->super_ready[k]) cudaEventDestroy(c->super_ready[k]);
+        if (c->super_free[k]) cudaEventDestroy(c->super_free[k]);
+    }
+    c->validate_bits.release();
+    if (c->validate_host) cudaFreeHost(c->validate_host);
+    pz_comm_destroy(c);
+    c->comm_send.release(); c->comm_recv.release();
+    if (c->comm_host) cudaFreeHost(c->comm_host);
     c->gscratch.release(); c->rows.release(); c->acc.release(); c->span_cum.release();
     c->fin.release(); c->arrays.release(); c->ps_dev.release(); c->band_lo.release();
     c->band_hi.release(); c->tband_lo.release(); c->tband_hi.release(); c->canon_flags.release();
@@ -410,14 +459,23 @@ static int sweep_chunk(pz_ctx *c, pz_ctx::Slot &sl, cudaStream_t sp, int32_t R, 
             }
             int l = 0;
             PhaseTimer t(c, PZ_PHASE_PERM, sp);
-            if (perm_mode == PZ_PERM_PHILOX)
-                PZ_CUDA(launch_perm_philox(M, R, seeds_dev, sl.perms.p, sp, &l));
-            else if (perm_mode == PZ_PERM_FEISTEL)
-                PZ_CUDA(launch_perm_feistel(M, R, seeds_dev, sl.perms.p, sp, &l));
-            else
-                PZ_CUDA(launch_perm_mt19937(M, R, seeds_dev, sl.perms.p, sp, &l));
+            PZ_CUDA(launch_perm_mode(perm_mode, M, R, seeds_dev, sl.perms.p, sp, &l));
             c->launches += l;
         }
+    }
+    if ((perm_mode == PZ_PERM_HOST || perm_mode == PZ_PERM_DEVICE) && !c->trusted_orders && M > 0 && R > 0) {
+        // caller-supplied orders: range and permutation check before anything indexes with them
+        const size_t words = (size_t)R * (((size_t)M + 31) / 32) + 1;
+        PZ_CUDA(c->validate_bits.ensure(words));
+        int *flag = reinterpret_cast<int *>(c->validate_bits.p + (words - 1));
+        PZ_CUDA(launch_validate_orders(M, R, perms_dev, c->validate_bits.p, flag, sp));
+        c->launches += 1;
+        PZ_CUDA(cudaMemcpyAsync(c->validate_host, flag, sizeof(int), cudaMemcpyDeviceToHost, sp));
+        PZ_CUDA(cudaStreamSynchronize(sp));
+        if (*c->validate_host & 1)
+            return fail(PZ_ERR_ARG, "bond order entry outside [0, num_edges)");
+        if (*c->validate_host & 2)
+            return fail(PZ_ERR_ARG, "bond order is not a permutation (repeated entry)");
     }
     SweepPlan plan = plan_sweep(c->N, R, c->sms, c->smem_optin, c->force_kind, c->team, c->claim_cap, c->cta_warps);
     if (plan.kind != STORE_G32 && c->N > 65536)
@@ -441,6 +499,7 @@ static int sweep_chunk(pz_ctx *c, pz_ctx::Slot &sl, cudaStream_t sp, int32_t R, 
     sa.nspan = sl.nspan.p;
     sa.gscratch = c->gscratch.p;
     sa.claim_log2 = plan.claim_log2;
+    sa.epoch_start = c->epoch_start;
     {
         PhaseTimer t(c, PZ_PHASE_SWEEP);
         PZ_CUDA(launch_sweep(plan, sa, c->stream));
@@ -461,7 +520,7 @@ static int check_run_args(pz_ctx *c, int32_t R, int perm_mode, const void *perm_
     if (c->N == 0) return fail(PZ_ERR_STATE, "no graph set (call pz_set_graph first)");
     if (R < 0) return fail(PZ_ERR_ARG, "R must be >= 0");
     const int base_mode = perm_mode & ~PZ_SEEDS_ON_DEVICE;
-    if (base_mode < PZ_PERM_HOST || base_mode > PZ_PERM_FEISTEL)
+    if (base_mode < PZ_PERM_HOST || base_mode > PZ_PERM_PHILOX_FY)
         return fail(PZ_ERR_ARG, "unknown perm_mode");
     if ((perm_mode & PZ_SEEDS_ON_DEVICE) && base_mode < PZ_PERM_MT19937)
         return fail(PZ_ERR_ARG, "PZ_SEEDS_ON_DEVICE needs a device RNG mode");
@@ -510,7 +569,8 @@ int pz_run_rows(pz_ctx *c, int32_t R, int perm_mode, const void *perm_src, void 
 // ---------------------------------------------------------------------------
 static int ensure_acc(pz_ctx *c)
 {
-    const size_t words = ((size_t)c->M + 1) * PZ_ACC_WORDS;
+    // (+ one word behind the block: the run count travels with the cross-GPU all-reduce)
+    const size_t words = ((size_t)c->M + 1) * PZ_ACC_WORDS + 1;
     if (c->acc.cap < words) {
         PZ_CUDA(c->acc.ensure(words));
         PZ_CUDA(cudaMemsetAsync(c->acc.p, 0, words * 8, c->stream));
@@ -547,7 +607,7 @@ int pz_make_perms(pz_ctx *c, int32_t R, int perm_mode, const uint32_t *seeds, in
 {
     if (!c) return fail(PZ_ERR_ARG, "null context");
     if (c->N == 0) return fail(PZ_ERR_STATE, "no graph set (call pz_set_graph first)");
-    if (perm_mode != PZ_PERM_MT19937 && perm_mode != PZ_PERM_PHILOX && perm_mode != PZ_PERM_FEISTEL)
+    if (perm_mode < PZ_PERM_MT19937 || perm_mode > PZ_PERM_PHILOX_FY)
         return fail(PZ_ERR_ARG, "pz_make_perms: perm_mode must be a device RNG mode");
     if (R < 0 || (R > 0 && (!seeds || !out))) return fail(PZ_ERR_ARG, "pz_make_perms: bad arguments");
     if (R == 0 || c->M == 0) return PZ_OK;
@@ -565,9 +625,7 @@ int pz_make_perms(pz_ctx *c, int32_t R, int perm_mode, const uint32_t *seeds, in
         int l = 0;
         {
             PhaseTimer t(c, PZ_PHASE_PERM);
-            if (perm_mode == PZ_PERM_PHILOX) PZ_CUDA(launch_perm_philox(c->M, n, sl.seeds.p, dst, c->stream, &l));
-            else if (perm_mode == PZ_PERM_FEISTEL) PZ_CUDA(launch_perm_feistel(c->M, n, sl.seeds.p, dst, c->stream, &l));
-            else PZ_CUDA(launch_perm_mt19937(c->M, n, sl.seeds.p, dst, c->stream, &l));
+            PZ_CUDA(launch_perm_mode(perm_mode, c->M, n, sl.seeds.p, dst, c->stream, &l));
         }
         c->launches += l;
         if (!is_device)
@@ -613,32 +671,90 @@ int pz_run_fused(pz_ctx *c, int32_t R, int perm_mode, const void *perm_src, int 
     if ((flags & PZ_FUSE_CANON) && (c->num_p == 0 || c->pmf_M != c->M || c->sf_M != c->M))
         return fail(PZ_ERR_STATE, "pz_run_fused: PZ_FUSE_CANON needs pz_set_ps(M = bonds of the graph) first");
     PZ_CUDA(cudaSetDevice(c->device));
-    if ((perm_mode & ~PZ_SEEDS_ON_DEVICE) == PZ_PERM_MT19937 && R > 0 && c->M > 0) {
-        // numpy's stream is one serial chain per run (one thread each, a random access per
-        // step): its throughput comes from the number of runs in flight, not from the chunk of
-        // the sweep.  Bond orders are therefore generated for as many runs at once as half the
-        // scratch budget holds, then swept chunk by chunk from device memory.
+    const int base_mode = perm_mode & ~PZ_SEEDS_ON_DEVICE;
+    if ((base_mode == PZ_PERM_MT19937 || base_mode == PZ_PERM_PHILOX_FY) && R > 0 && c->M > 0) {
+        // Thread-per-run generators: the shuffle is one serial chain per run (a random access per
+        // step), so throughput comes from the number of runs in flight, not from the chunk of the
+        // sweep.  Bond orders are generated a SUPER-CHUNK of runs at a time into one of two
+        // buffers on the bond-order stream; the kernels use no shared memory and few registers,
+        // so super-chunk k+1 is generated on the SMs that sweep super-chunk k (the sweep is bound
+        // by shared-memory latency, the shuffle by random DRAM sectors).  Only the first
+        // super-chunk has nothing to hide behind: it is kept short.
         const size_t per = (size_t)c->M * 4;
-        const size_t super = std::max<size_t>(1, std::min<size_t>((size_t)R, (c->chunk_bytes / 2) / per));
-        for (size_t s0 = 0; s0 < (size_t)R; s0 += super) {
-            const int32_t sn = (int32_t)std::min(super, (size_t)R - s0);
-            const uint32_t *seeds_dev = (const uint32_t *)perm_src + s0;
-            if (!(perm_mode & PZ_SEEDS_ON_DEVICE)) {
-                PZ_CUDA(c->seed_super.ensure((size_t)sn));
-                PZ_CUDA(cudaMemcpyAsync(c->seed_super.p, (const uint32_t *)perm_src + s0, (size_t)sn * 4,
-                                        cudaMemcpyHostToDevice, c->stream));
-                seeds_dev = c->seed_super.p;
+        const size_t cap = (size_t)perm_serial_capacity(c->sms);        // runs of one co-resident launch
+        size_t super = std::max<size_t>(1, std::min<size_t>(cap, (c->chunk_bytes / 4) / per));
+        if (const char *e = getenv("PZ_SUPER_RUNS")) super = std::max<size_t>(1, (size_t)atoll(e));
+        const bool overlap = c->pipeline != 0;
+        std::vector<size_t> sizes;
+        {
+            // A short first super-chunk (its generation is exposed), then a geometric ramp: the
+            // generation of super-chunk k+1 has to fit under the sweeps and statistics of k, and
+            // it proceeds at roughly 1.5x their pace.  Whole waves of the sweep (multiples of the
+            // SM count).
+            const size_t sms = (size_t)std::max(c->sms, 1);
+            auto waves = [&](size_t x) { return std::max(sms, (x + sms - 1) / sms * sms); };
+            size_t rem = (size_t)R;
+            size_t next = std::min(super, waves(std::max<size_t>(sms * 4, (size_t)R / 16)));
+            if (!overlap) next = super;
+            while (rem > 0) {
+                size_t take = std::min(rem, next);
+                if (rem - take < take / 2) take = rem <= super ? rem : take;   // no short tail
+                sizes.push_back(take);
+                rem -= take;
+                next = std::min(super, waves(next + next / 2));
             }
-            PZ_CUDA(c->perm_super.ensure((size_t)sn * c->M));
+        }
+        cudaStream_t sg = overlap ? c->s_perm : c->stream;
+        auto generate = [&](size_t k, size_t s0) -> int {
+            const int b = (int)(k & 1);
+            const int32_t sn = (int32_t)sizes[k];
+            const uint32_t *seeds_dev = (const uint32_t *)perm_src + s0;
+            if (k >= 2 && overlap) PZ_CUDA(cudaStreamWaitEvent(sg, c->super_free[b], 0));
+            if (!(perm_mode & PZ_SEEDS_ON_DEVICE)) {
+                PZ_CUDA(c->seed_super[b].ensure((size_t)sn));
+                PZ_CUDA(cudaMemcpyAsync(c->seed_super[b].p, (const uint32_t *)perm_src + s0, (size_t)sn * 4,
+                                        cudaMemcpyHostToDevice, sg));
+                seeds_dev = c->seed_super[b].p;
+            }
+            PZ_CUDA(c->perm_super[b].ensure((size_t)sn * c->M));
             int l = 0;
             {
-                PhaseTimer t(c, PZ_PHASE_PERM);
-                PZ_CUDA(launch_perm_mt19937(c->M, sn, seeds_dev, c->perm_super.p, c->stream, &l));
+                PhaseTimer t(c, PZ_PHASE_PERM, sg);
+                PZ_CUDA(launch_perm_mode(base_mode, c->M, sn, seeds_dev, c->perm_super[b].p, sg, &l));
             }
             c->launches += l;
-            rc = pz_run_fused(c, sn, PZ_PERM_DEVICE, c->perm_super.p, flags);
-            if (rc) return rc;
+            if (overlap) PZ_CUDA(cudaEventRecord(c->super_ready[b], sg));
+            return PZ_OK;
+        };
+        // (buffers are sized before anything is in flight: ensure() may free and reallocate)
+        for (int b = 0; b < 2 && b < (int)sizes.size(); ++b) {
+            size_t need = 0;
+            for (size_t k = b; k < sizes.size(); k += 2) need = std::max(need, sizes[k]);
+            PZ_CUDA(c->perm_super[b].ensure(need * c->M));
+            if (!(perm_mode & PZ_SEEDS_ON_DEVICE)) PZ_CUDA(c->seed_super[b].ensure(need));
         }
+        PZ_CUDA(cudaStreamSynchronize(c->stream));
+        std::vector<size_t> offs(sizes.size() + 1, 0);
+        for (size_t k = 0; k < sizes.size(); ++k) offs[k + 1] = offs[k] + sizes[k];
+        rc = generate(0, 0); if (rc) return rc;
+        for (size_t k = 0; k < sizes.size(); ++k) {
+            const int b = (int)(k & 1);
+            if (overlap) {
+                PZ_CUDA(cudaStreamWaitEvent(c->stream, c->super_ready[b], 0));
+                // the next super-chunk goes to the bond-order stream BEFORE the sweeps of this one
+                // are launched, so its (few, small) CTAs are resident when the sweep CTAs arrive
+                if (k + 1 < sizes.size()) { rc = generate(k + 1, offs[k + 1]); if (rc) return rc; }
+            }
+            const bool was = c->trusted_orders;
+            c->trusted_orders = true;
+            rc = pz_run_fused(c, (int32_t)sizes[k], PZ_PERM_DEVICE, c->perm_super[b].p, flags);
+            c->trusted_orders = was;
+            if (rc) return rc;
+            if (overlap) PZ_CUDA(cudaEventRecord(c->super_free[b], c->stream));
+            else if (k + 1 < sizes.size()) { rc = generate(k + 1, offs[k + 1]); if (rc) return rc; }
+        }
+        PZ_CUDA(cudaStreamSynchronize(sg));
+        if (c->profiling) collect_phases(c);
         return PZ_OK;
     }
     if (flags & PZ_FUSE_MICRO) { rc = ensure_acc(c); if (rc) return rc; }
@@ -646,12 +762,23 @@ int pz_run_fused(pz_ctx *c, int32_t R, int perm_mode, const void *perm_src, int 
     // be visible to the side streams
     PZ_CUDA(cudaStreamSynchronize(c->stream));
     const int P = c->num_p;
-    const int pipeline = c->pipeline >= 0 ? c->pipeline
-                         : ((perm_mode & ~PZ_SEEDS_ON_DEVICE) == PZ_PERM_FEISTEL ? 2 : 0);
-    const int nslot = pipeline ? pz_ctx::PZ_SLOTS : 1;
+    const int pipeline = (base_mode == PZ_PERM_HOST || base_mode == PZ_PERM_DEVICE) ? 0
+                         : c->pipeline >= 0 ? c->pipeline
+                         : (base_mode == PZ_PERM_FEISTEL ? 2 : 0);
+    // three slots rotate even on one stream: the host then runs up to two chunks ahead of the
+    // device instead of waiting for every chunk's statistics before it launches the next sweep
+    const int nslot = pz_ctx::PZ_SLOTS;
+    const bool hide = pipeline != 0;          // bond orders are generated underneath the previous sweep
     const size_t per_run = (size_t)std::max(c->M, 1) * 12 + 4096 +   // orders + widest records
                            ((size_t)c->M / c->ckpt_every + 1) * 32;  // + checkpoints
-    size_t chunk = std::max<size_t>(1, (c->chunk_bytes / pz_ctx::PZ_SLOTS) / per_run);
+    // the global-memory store keeps one parent array per resident sweep CTA next to the slots
+    size_t budget = c->chunk_bytes;
+    {
+        const SweepPlan p0 = plan_sweep(c->N, R, c->sms, c->smem_optin, c->force_kind, c->team,
+                                        c->claim_cap, c->cta_warps);
+        budget = p0.gscratch_bytes < budget / 2 ? budget - p0.gscratch_bytes : budget / 2;
+    }
+    size_t chunk = std::max<size_t>(1, (budget / pz_ctx::PZ_SLOTS) / per_run);
     // Chunk sizes: whole waves (one run per sweep CTA, grid = a multiple of the SM count), as few
     // equal chunks as the scratch allows.  With the bond orders on their own stream: at least three
     // chunks (all but the first chunk's orders are generated underneath a sweep; never fewer than
@@ -665,7 +792,7 @@ int pz_run_fused(pz_ctx *c, int32_t R, int perm_mode, const void *perm_src, int 
         const size_t sms = (size_t)std::max(c->sms, 1);
         size_t rem = (size_t)R;
         size_t k = std::max<size_t>(1, (rem + chunk - 1) / chunk);
-        if (nslot > 1 && k >= 3) {
+        if (hide && k >= 3) {
             size_t last = 0;
             for (size_t ramp = 4 * sms; ramp < chunk && rem > 4 * ramp; ramp *= 3) {
                 sizes.push_back(ramp);
@@ -676,7 +803,7 @@ int pz_run_fused(pz_ctx *c, int32_t R, int perm_mode, const void *perm_src, int 
             // (generating the orders of a run takes about a fifth of sweeping it: a chunk of up to
             // four times the previous one still hides its orders)
             if (last) k = std::max(k, (rem + 4 * last - 1) / (4 * last));
-        } else if (nslot > 1) {
+        } else if (hide) {
             k = std::max<size_t>(k, std::min<size_t>(3, rem / (16 * sms)));
             k = std::max<size_t>(k, 1);
         }
@@ -951,6 +1078,8 @@ int pz_canon_reset(pz_ctx *c)
     return PZ_OK;
 }
 
+int32_t pz_canon_last_count(const pz_ctx *c) { return c ? c->canon_last_R : 0; }
+
 int pz_canon_last_runs(pz_ctx *c, double *out)
 {
     if (!c || !out) return fail(PZ_ERR_ARG, "pz_canon_last_runs: bad arguments");
@@ -1005,6 +1134,182 @@ int pz_timer_stop(pz_ctx *c, double *ms_out)
     float ms = 0.f;
     PZ_CUDA(cudaEventElapsedTime(&ms, c->timer_a, c->timer_b));
     *ms_out = ms;
+    return PZ_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// cross-GPU exchange: one process per GPU, NCCL over NVLink / NVSwitch.
+// The reference reduces the per-task results of a study with bond_reduce over pickles on a
+// shared file system (percolate/share/jugfile.py:126-135, 240-244); here every rank folds its
+// runs into its context and ONE collective step combines the ranks.  NCCL is loaded at run time
+// (dlopen): single-GPU users do not need it, and inside a PyTorch process the copy torch has
+// already loaded is the one that is found.
+// ---------------------------------------------------------------------------
+#include <dlfcn.h>
+#include <nccl.h>
+#include <mutex>
+
+namespace {
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    std::string why;
+};
+NcclApi g_nccl;
+std::once_flag g_nccl_once;
+
+void load_nccl()
+{
+    const char *names[] = {getenv("PZ_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+        if (!nm || !*nm) continue;
+        g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+        g_nccl.why = dlerror();
+    }
+    if (!g_nccl.lib) return;
+#define PZ_SYM(field, name)                                                        \
+    g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(g_nccl.lib, name)); \
+    if (!g_nccl.field) { g_nccl.why = std::string("missing symbol ") + name; g_nccl.lib = nullptr; return; }
+    PZ_SYM(GetUniqueId, "ncclGetUniqueId")
+    PZ_SYM(CommInitRank, "ncclCommInitRank")
+    PZ_SYM(CommDestroy, "ncclCommDestroy")
+    PZ_SYM(AllReduce, "ncclAllReduce")
+    PZ_SYM(AllGather, "ncclAllGather")
+    PZ_SYM(GroupStart, "ncclGroupStart")
+    PZ_SYM(GroupEnd, "ncclGroupEnd")
+    PZ_SYM(GetErrorString, "ncclGetErrorString")
+#undef PZ_SYM
+}
+
+int need_nccl()
+{
+    std::call_once(g_nccl_once, load_nccl);
+    if (!g_nccl.lib) return fail(PZ_ERR_STATE, "NCCL could not be loaded: " + g_nccl.why);
+    return PZ_OK;
+}
+}  // namespace
+
+#define PZ_NCCL(expr)                                                                     \
+    do {                                                                                  \
+        ncclResult_t _r = (expr);                                                         \
+        if (_r != ncclSuccess)                                                            \
+            return fail(PZ_ERR_CUDA, std::string(#expr) + ": " + g_nccl.GetErrorString(_r)); \
+    } while (0)
+
+extern "C" {
+
+int pz_comm_unique_id(void *id_out)
+{
+    if (!id_out) return fail(PZ_ERR_ARG, "pz_comm_unique_id: id_out is NULL");
+    int rc = need_nccl(); if (rc) return rc;
+    static_assert(sizeof(ncclUniqueId) == PZ_COMM_ID_BYTES, "PZ_COMM_ID_BYTES");
+    ncclUniqueId id;
+    PZ_NCCL(g_nccl.GetUniqueId(&id));
+    memcpy(id_out, &id, sizeof(id));
+    return PZ_OK;
+}
+
+int pz_comm_init(pz_ctx *c, int world, int rank, const void *id)
+{
+    if (!c || !id || world < 1 || rank < 0 || rank >= world)
+        return fail(PZ_ERR_ARG, "pz_comm_init: bad arguments");
+    int rc = need_nccl(); if (rc) return rc;
+    PZ_CUDA(cudaSetDevice(c->device));
+    pz_comm_destroy(c);
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    ncclComm_t comm = nullptr;
+    PZ_NCCL(g_nccl.CommInitRank(&comm, world, uid, rank));
+    c->comm = comm;
+    c->comm_world = world;
+    c->comm_rank = rank;
+    return PZ_OK;
+}
+
+int pz_comm_destroy(pz_ctx *c)
+{
+    if (!c) return fail(PZ_ERR_ARG, "null context");
+    if (c->comm && g_nccl.lib) {
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+        g_nccl.CommDestroy((ncclComm_t)c->comm);
+    }
+    c->comm = nullptr;
+    c->comm_world = 1;
+    c->comm_rank = 0;
+    return PZ_OK;
+}
+
+int pz_comm_world(const pz_ctx *c) { return c && c->comm ? c->comm_world : 1; }
+int pz_comm_rank(const pz_ctx *c) { return c && c->comm ? c->comm_rank : 0; }
+
+int pz_allreduce(pz_ctx *c)
+{
+    if (!c) return fail(PZ_ERR_ARG, "null context");
+    if (!c->comm) return fail(PZ_ERR_STATE, "pz_allreduce: call pz_comm_init first");
+    if (c->N == 0) return fail(PZ_ERR_STATE, "no graph set");
+    PZ_CUDA(cudaSetDevice(c->device));
+    ncclComm_t comm = (ncclComm_t)c->comm;
+    const int W = c->comm_world;
+    int rc = ensure_acc(c); if (rc) return rc;
+    const size_t words = ((size_t)c->M + 1) * PZ_ACC_WORDS;
+    const size_t cols = (size_t)c->num_p * PZ_CANON_COLS;
+    const size_t pay = 1 + 2 * cols;                        // count, mean[cols], M2[cols]
+    const size_t host_need = 1 + pay + (size_t)W * pay;     // run count word + send + recv
+    if (c->comm_host_cap < host_need) {
+        if (c->comm_host) cudaFreeHost(c->comm_host);
+        c->comm_host = nullptr; c->comm_host_cap = 0;
+        PZ_CUDA(cudaMallocHost(&c->comm_host, host_need * 8));
+        c->comm_host_cap = host_need;
+    }
+    // the run count rides in the word behind the accumulator block: one integer all-reduce
+    int64_t *runs_word = reinterpret_cast<int64_t *>(c->comm_host);
+    *runs_word = c->micro_runs;
+    PZ_CUDA(cudaMemcpyAsync(c->acc.p + words, runs_word, 8, cudaMemcpyHostToDevice, c->stream));
+    double *send_h = c->comm_host + 1, *recv_h = c->comm_host + 1 + pay;
+    if (cols) {
+        send_h[0] = (double)c->canon_count;
+        for (size_t i = 0; i < cols; ++i) {
+            send_h[1 + i] = c->canon_count ? c->canon_mean[i] : 0.0;
+            send_h[1 + cols + i] = c->canon_count ? c->canon_m2[i] : 0.0;
+        }
+        PZ_CUDA(c->comm_send.ensure(pay));
+        PZ_CUDA(c->comm_recv.ensure((size_t)W * pay));
+        PZ_CUDA(cudaMemcpyAsync(c->comm_send.p, send_h, pay * 8, cudaMemcpyHostToDevice, c->stream));
+    }
+    PZ_NCCL(g_nccl.GroupStart());
+    // exact: every accumulator word holds a 32-bit limb, so the word-wise sum cannot carry
+    PZ_NCCL(g_nccl.AllReduce(c->acc.p, c->acc.p, words + 1, ncclInt64, ncclSum, comm, c->stream));
+    if (cols)
+        PZ_NCCL(g_nccl.AllGather(c->comm_send.p, c->comm_recv.p, pay, ncclFloat64, comm, c->stream));
+    PZ_NCCL(g_nccl.GroupEnd());
+    PZ_CUDA(cudaMemcpyAsync(runs_word, c->acc.p + words, 8, cudaMemcpyDeviceToHost, c->stream));
+    if (cols)
+        PZ_CUDA(cudaMemcpyAsync(recv_h, c->comm_recv.p, (size_t)W * pay * 8, cudaMemcpyDeviceToHost, c->stream));
+    PZ_CUDA(cudaStreamSynchronize(c->stream));
+    c->launches += cols ? 2 : 1;
+    c->micro_runs = *runs_word;
+    if (cols) {
+        // rank-ordered Chan merge (the arithmetic of bond_reduce): bit-identical on every rank
+        c->canon_count = 0;
+        c->canon_mean.assign(cols, 0.0);
+        c->canon_m2.assign(cols, 0.0);
+        for (int r = 0; r < W; ++r) {
+            const double *p = recv_h + (size_t)r * pay;
+            chan_merge(c->canon_count, c->canon_mean, c->canon_m2, (int64_t)llround(p[0]), p + 1, p + 1 + cols);
+        }
+    }
     return PZ_OK;
 }
 

@@ -22,6 +22,7 @@ struct SweepArgs {
     uint32_t *nspan;          // [R] first n with a spanning cluster (NSPAN_NEVER if none)
     uint32_t *gscratch;       // STORE_G32: [total warps][N]
     int claim_log2;           // log2 of the per-warp claim table (entries)
+    uint32_t epoch_start;     // first claim epoch of a run (22 bits; PZ_EPOCH_START shortens it for tests)
 };
 
 struct SweepPlan {

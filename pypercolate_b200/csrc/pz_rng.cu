@@ -38,6 +38,8 @@
 //    uniform distribution over ALL permutations on small domains and by order
 //    statistics on large ones, tests/test_gpu_parity.py against the reference's
 //    confidence intervals.
+#include <cstdlib>
+#include <algorithm>
 #include "pz_common.cuh"
 #include "pz_internal.h"
 
@@ -356,102 +358,250 @@ __global__ void iota_rows_kernel(int32_t M, int32_t R, int32_t *perms)
 }
 
 // One thread per run.  The shuffle is a serial chain, but only through memory: the
-// target j of step i comes from the twister alone, so the targets of the next MTQ steps
+// target j of step i comes from the generator alone, so the targets of the next SWQ steps
 // are drawn ahead of time and their x[j] loads are in flight while the current step
 // swaps.  A step that writes a position a queued load has already read (its own target j,
 // which now holds the old x[i]) forwards the new value to that queue entry, so the result
 // is exactly the sequential one.
+//
+// The queue is a shift register of SWQ (target, prefetched value) pairs, head at index 0,
+// empty entries marked by target -1.  push() executes the head's step (if any), shifts,
+// and appends the new target at the tail; SWQ pushes of the empty marker drain it.
 #ifndef PZ_MTQ
 #define PZ_MTQ 8
 #endif
-static constexpr int MTQ = PZ_MTQ;
+static constexpr int SWQ = PZ_MTQ;
 
+struct SwapQueue {
+    int32_t jq[SWQ], vq[SWQ];
+    int32_t *x;
+    int32_t i;                           // step the head entry belongs to
+    __device__ __forceinline__ void init(int32_t *x_, int32_t M) {
+        x = x_; i = M - 1;
+#pragma unroll
+        for (int k = 0; k < SWQ; ++k) { jq[k] = -1; vq[k] = 0; }
+    }
+    // j < 0: the empty marker (drains the queue)
+    __device__ __forceinline__ void push(int32_t jn) {
+        const int32_t j = jq[0];
+        int32_t a = 0;
+        if (j >= 0) {                    // step i: swap x[i] and x[j]
+            a = x[i];
+            const int32_t b = (j == i) ? a : vq[0];
+            x[i] = b;
+            x[j] = a;
+            --i;
+            // x[i] runs down the row one element per step: fetch its line ahead of the dependent load
+            if ((i & 7) == 7 && i >= 64)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(x + (i - 64)));
+        }
+        // shift, forwarding this step's write of x[j] to loads that came too early
+        // (a queued target is below i, so it never equals position i)
+#pragma unroll
+        for (int k = 0; k + 1 < SWQ; ++k) {
+            const int32_t jj = jq[k + 1];
+            int32_t vv = vq[k + 1];
+            if (jj == j) vv = a;
+            jq[k] = jj; vq[k] = vv;
+        }
+        jq[SWQ - 1] = jn;
+        vq[SWQ - 1] = jn >= 0 ? x[jn] : 0;     // behind this step's stores in program order
+    }
+    __device__ __forceinline__ void drain() {
+#pragma unroll 1
+        for (int k = 0; k < SWQ; ++k) push(-1);
+    }
+};
+
+// NumPy's stream.  The twister state of a run is one CONTIGUOUS 2.5 KB row of global memory
+// (thread-local arrays are interleaved word by word across the lanes of a warp, and lanes that
+// have rejected different numbers of draws then touch 32 different lines per access).  The state
+// is advanced in place EIGHT words at a time -- element k of the next generation needs only
+// elements k, k+1 and k+397 (mod 624), so a block of eight is independent of itself -- instead
+// of all 624 at once: with the block regeneration of the textbook code every lane of a warp
+// reaches its regeneration at a different step (the lanes have rejected different numbers of
+// draws), each of those runs with one active lane, and the warp pays 32 serial regenerations
+// per 468 steps: that, not the shuffle, was 95 % of the kernel (8.6e9 bonds/s).
+// Every lane then looks at the same draw q of its block in lock step; a draw is either
+// accepted (masked value <= i: one shuffle step) or rejected (nothing happens), so there is
+// no rejection LOOP for lanes to diverge in.
 __global__ void __launch_bounds__(64) perm_mt19937_kernel(int32_t M, int32_t R, const uint32_t *seeds,
                                                            int32_t *perms, uint32_t *states)
 {
-    const int run = blockIdx.x * blockDim.x + threadIdx.x;
-    if (run >= R) return;
-    // the twister state of a run is one CONTIGUOUS 2.5 KB row of global memory: thread-local
-    // arrays are interleaved word by word across the lanes of a warp, and lanes that have
-    // rejected different numbers of draws then touch 32 different lines per access with no
-    // reuse (measured: 8x the DRAM traffic of the shuffle itself)
-    uint32_t *mt = states + (size_t)run * 624;
-    {
-        uint32_t v = seeds[run];
-        mt[0] = v;
-        for (int i = 1; i < 624; ++i) { v = 1812433253u * (v ^ (v >> 30)) + (uint32_t)i; mt[i] = v; }
-    }
-    int idx = 624;
-    int32_t *x = perms + (size_t)run * M;
-
-    // j for step i: masked rejection in [0, i] (numpy legacy rk_interval)
-    auto draw = [&](int32_t i) -> int32_t {
-        uint32_t mask = (uint32_t)i;
-        mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
-        uint32_t j;
-        do {
-            if (idx >= 624) {
-                for (int k = 0; k < 624; ++k) {
-                    const uint32_t y = (mt[k] & 0x80000000u) | (mt[k == 623 ? 0 : k + 1] & 0x7fffffffu);
-                    mt[k] = mt[k + 397 < 624 ? k + 397 : k + 397 - 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-                }
-                idx = 0;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    for (int run = tid; run < R; run += nthr) {
+        uint32_t *mt = states + (size_t)tid * 624;
+        {
+            uint32_t v = seeds[run];
+            mt[0] = v;
+            for (int i = 1; i < 624; ++i) { v = 1812433253u * (v ^ (v >> 30)) + (uint32_t)i; mt[i] = v; }
+        }
+        int k0 = 0;                          // next block of the state row (multiple of 8)
+        SwapQueue q;
+        q.init(perms + (size_t)run * M, M);
+        int32_t i_fill = M - 1;              // next step to draw a target for
+        while (i_fill >= 1) {
+            uint32_t a[9], d[8];
+            {
+                const uint4 lo = *reinterpret_cast<const uint4 *>(mt + k0);
+                const uint4 hi = *reinterpret_cast<const uint4 *>(mt + k0 + 4);
+                a[0] = lo.x; a[1] = lo.y; a[2] = lo.z; a[3] = lo.w;
+                a[4] = hi.x; a[5] = hi.y; a[6] = hi.z; a[7] = hi.w;
+                a[8] = mt[k0 + 8 == 624 ? 0 : k0 + 8];
             }
-            uint32_t y = mt[idx++];
-            y ^= (y >> 11);
-            y ^= (y << 7) & 0x9d2c5680u;
-            y ^= (y << 15) & 0xefc60000u;
-            y ^= (y >> 18);
-            j = y & mask;
-        } while (j > (uint32_t)i);
-        return (int32_t)j;
-    };
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                int km = k0 + e + 397;
+                if (km >= 624) km -= 624;
+                const uint32_t y = (a[e] & 0x80000000u) | (a[e + 1] & 0x7fffffffu);
+                d[e] = mt[km] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            *reinterpret_cast<uint4 *>(mt + k0) = make_uint4(d[0], d[1], d[2], d[3]);
+            *reinterpret_cast<uint4 *>(mt + k0 + 4) = make_uint4(d[4], d[5], d[6], d[7]);
+            k0 = k0 + 8 == 624 ? 0 : k0 + 8;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                uint32_t y = d[e];
+                y ^= (y >> 11);
+                y ^= (y << 7) & 0x9d2c5680u;
+                y ^= (y << 15) & 0xefc60000u;
+                y ^= (y >> 18);
+                if (i_fill >= 1) {
+                    // numpy legacy rk_interval: smallest 2^k - 1 >= i, masked rejection
+                    const uint32_t j = y & (0xffffffffu >> __clz(i_fill));
+                    if (j <= (uint32_t)i_fill) { q.push((int32_t)j); --i_fill; }
+                }
+            }
+        }
+        q.drain();
+    }
+}
 
-    int32_t jq[MTQ], vq[MTQ];            // targets and prefetched values of steps i, i-1, ..., i-MTQ+1
-    int32_t i_fill = M - 1;              // next step to draw a target for
+// Textbook Fisher-Yates with counter-based draws (PZ_PERM_PHILOX_FY): for i = M-1 .. 1,
+// j = unbiased (Lemire) draw in [0, i] from word i & 3 of Philox4x32-10 counter (i >> 2, 0, 0, 4)
+// under key (seed, 'PERC'); on the (rare, < 2^-15) Lemire rejection words 0.. of counters
+// (i, attempt >= 1, 0, 5).  One thread per run, no shared memory and no state: like the
+// MT19937 kernel it runs underneath the sweep of the previous batch of runs.
+// oracle/pz_oracle.c restates it on the CPU (philox_fy_permutation).
+__device__ __forceinline__ uint32_t philox_fy_bounded(uint32_t seed, uint32_t i, uint32_t w)
+{
+    const uint32_t range = i + 1u;
+    uint64_t m = (uint64_t)w * range;
+    if ((uint32_t)m >= range) return (uint32_t)(m >> 32);      // cannot be below the threshold
+    const uint32_t thresh = (0u - range) % range;
+    if ((uint32_t)m >= thresh) return (uint32_t)(m >> 32);
+    for (uint32_t attempt = 1;; ++attempt) {
+        uint32_t r[4];
+        philox4x32_10(seed, PHILOX_KEY1, i, attempt, 0u, 5u, r);
 #pragma unroll
-    for (int k = 0; k < MTQ; ++k) {
-        jq[k] = -1; vq[k] = 0;
-        if (i_fill >= 1) { jq[k] = draw(i_fill); vq[k] = x[jq[k]]; --i_fill; }
-    }
-    for (int32_t i = M - 1; i >= 1; --i) {
-        const int32_t j = jq[0];
-        const int32_t a = x[i];
-        const int32_t b = (j == i) ? a : vq[0];
-        x[i] = b;
-        x[j] = a;
-        // shift the queue, forwarding this step's two writes to loads that came too early
-#pragma unroll
-        for (int k = 0; k + 1 < MTQ; ++k) {
-            const int32_t jj = jq[k + 1];
-            int32_t vv = vq[k + 1];
-            if (jj == j) vv = a;         // (a queued target is < i, so it never equals position i)
-            jq[k] = jj; vq[k] = vv;
-        }
-        jq[MTQ - 1] = -1; vq[MTQ - 1] = 0;
-        if (i_fill >= 1) {
-            const int32_t jn = draw(i_fill);
-            jq[MTQ - 1] = jn;
-            vq[MTQ - 1] = x[jn];        // after this step's stores in program order: up to date as of now
-            --i_fill;
+        for (int e = 0; e < 4; ++e) {
+            m = (uint64_t)r[e] * range;
+            if ((uint32_t)m >= thresh) return (uint32_t)(m >> 32);
         }
     }
+}
+
+__global__ void __launch_bounds__(64) perm_philox_fy_kernel(int32_t M, int32_t R, const uint32_t *seeds,
+                                                             int32_t *perms)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    for (int run = tid; run < R; run += nthr) {
+        const uint32_t seed = seeds[run];
+        SwapQueue q;
+        q.init(perms + (size_t)run * M, M);
+        for (int32_t g = (M - 1) >> 2; g >= 0; --g) {
+            uint32_t o[4];
+            philox4x32_10(seed, PHILOX_KEY1, (uint32_t)g, 0u, 0u, 4u, o);
+#pragma unroll
+            for (int e = 3; e >= 0; --e) {
+                const int32_t i = 4 * g + e;
+                if (i >= 1 && i <= M - 1) q.push((int32_t)philox_fy_bounded(seed, (uint32_t)i, o[e]));
+            }
+        }
+        q.drain();
+    }
+}
+
+// runs of one launch of the thread-per-run kernels: at most SERIAL_CTAS_PER_SM CTAs of 64 threads
+// per SM, so that a sweep CTA (46 K registers, all of the shared memory) still fits next to them
+static constexpr int SERIAL_CTAS_PER_SM = 4;
+int perm_serial_capacity(int sms) { return sms * SERIAL_CTAS_PER_SM * 64; }
+
+static cudaError_t launch_perm_serial(int mode_mt, int32_t M, int32_t R, const uint32_t *seeds,
+                                      int32_t *perms, cudaStream_t s, int *launches)
+{
+    *launches = 0;
+    if (R <= 0 || M <= 0) return cudaSuccess;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int ctas = (R + 63) / 64;
+    // more runs than one co-resident launch holds: threads take several runs in turn
+    // (PZ_SERIAL_FULL=1: as many threads as runs -- when nothing has to fit next to the kernel)
+    static const bool full = getenv("PZ_SERIAL_FULL") && atoi(getenv("PZ_SERIAL_FULL"));
+    if (!full && ctas > sms * SERIAL_CTAS_PER_SM) ctas = sms * SERIAL_CTAS_PER_SM;
+    uint32_t *states = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (mode_mt) {
+        e = cudaMallocAsync(&states, (size_t)ctas * 64 * 624 * sizeof(uint32_t), s);
+        if (e != cudaSuccess) return e;
+    }
+    iota_rows_kernel<<<1184, 256, 0, s>>>(M, R, perms);
+    if (mode_mt) perm_mt19937_kernel<<<ctas, 64, 0, s>>>(M, R, seeds, perms, states);
+    else perm_philox_fy_kernel<<<ctas, 64, 0, s>>>(M, R, seeds, perms);
+    *launches = 2;
+    e = cudaGetLastError();
+    if (mode_mt) {
+        const cudaError_t e2 = cudaFreeAsync(states, s);
+        if (e == cudaSuccess) e = e2;
+    }
+    return e;
 }
 
 cudaError_t launch_perm_mt19937(int32_t M, int32_t R, const uint32_t *seeds, int32_t *perms,
                                 cudaStream_t s, int *launches)
 {
-    *launches = 0;
+    return launch_perm_serial(1, M, R, seeds, perms, s, launches);
+}
+
+cudaError_t launch_perm_philox_fy(int32_t M, int32_t R, const uint32_t *seeds, int32_t *perms,
+                                  cudaStream_t s, int *launches)
+{
+    return launch_perm_serial(0, M, R, seeds, perms, s, launches);
+}
+
+// ---------------------------------------------------------------------------
+// caller-supplied bond orders (PZ_PERM_HOST / PZ_PERM_DEVICE): every row must be a permutation
+// of 0..M-1 -- an entry outside the range would index the bond list out of bounds in the sweep,
+// a repeated one gives records that mean nothing.  flag bit 0: out of range, bit 1: repeated.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) validate_orders_kernel(int32_t M, int32_t R, const int32_t *perms,
+                                                              uint32_t *bitmap, int words, int *flag)
+{
+    for (int run = blockIdx.y; run < R; run += gridDim.y) {
+        const int32_t *row = perms + (size_t)run * M;
+        uint32_t *bits = bitmap + (size_t)run * words;
+        int bad = 0;
+        for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < M; n += gridDim.x * blockDim.x) {
+            const uint32_t e = (uint32_t)row[n];
+            if (e >= (uint32_t)M) { bad |= 1; continue; }
+            const uint32_t bit = 1u << (e & 31u);
+            if (atomicOr(&bits[e >> 5], bit) & bit) bad |= 2;
+        }
+        if (bad) atomicOr(flag, bad);
+    }
+}
+
+cudaError_t launch_validate_orders(int32_t M, int32_t R, const int32_t *perms, uint32_t *bitmap,
+                                   int *flag, cudaStream_t s)
+{
     if (R <= 0 || M <= 0) return cudaSuccess;
-    uint32_t *states = nullptr;
-    cudaError_t e = cudaMallocAsync(&states, (size_t)R * 624 * sizeof(uint32_t), s);
+    const int words = (M + 31) / 32;
+    cudaError_t e = cudaMemsetAsync(bitmap, 0, ((size_t)R * words + 1) * 4, s);
     if (e != cudaSuccess) return e;
-    iota_rows_kernel<<<1184, 256, 0, s>>>(M, R, perms);
-    perm_mt19937_kernel<<<(R + 63) / 64, 64, 0, s>>>(M, R, seeds, perms, states);
-    *launches = 2;
-    e = cudaGetLastError();
-    const cudaError_t e2 = cudaFreeAsync(states, s);
-    return e != cudaSuccess ? e : e2;
+    dim3 grid((unsigned)std::min(64, (M + 255) / 256), (unsigned)std::min(R, 16384));
+    validate_orders_kernel<<<grid, 256, 0, s>>>(M, R, perms, bitmap, words, flag);
+    return cudaGetLastError();
 }
 
 }  // namespace pz

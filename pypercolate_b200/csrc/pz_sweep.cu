@@ -31,6 +31,9 @@
 namespace pz {
 
 static constexpr uint32_t CLAIM_FREE = 0xffffffffu;
+// claim keys = (epoch << 10) | position in the batch; the epoch counts down one per round and is
+// rebased (claim table cleared) at a batch boundary once it drops below EPOCH_LOW
+static constexpr uint32_t EPOCH_LOW = 0x00001000u;      // (first epoch: SweepArgs::epoch_start)
 #ifndef PZ_STRICT_FENCE
 #define PZ_STRICT_FENCE 0
 #endif
@@ -487,7 +490,7 @@ __global__ void __launch_bounds__(32 * CTA_WARPS, 1) sweep_cta_kernel(SweepArgs 
         const int32_t *perm = a.perms + (size_t)run * M;
         Rec *rec_out = reinterpret_cast<Rec *>(a.recs) + (size_t)run * M;
         bool track = spanning;                 // CTA-uniform
-        uint32_t epoch = 0x003fffffu;          // decreasing: newer claims always win over stale ones
+        uint32_t epoch = a.epoch_start;        // decreasing: newer claims always win over stale ones
 #ifdef PZ_TIMING
         long long tm_find = 0, tm_init = clock64(), tm_rounds = 0, tm_t = 0, tm_seg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tm_p = 0, tm_star = 0, tm_late = 0, tm_nlate = 0, tm_b0 = 0; int tm_pc = 0;
 #define TM(k) { const long long _c = clock64(); tm_seg[k] += _c - tm_p; tm_p = _c; }
@@ -507,6 +510,15 @@ __global__ void __launch_bounds__(32 * CTA_WARPS, 1) sweep_cta_kernel(SweepArgs 
             const Edge uv = uv_next;
             if (n + CTA_THREADS < M) uv_next = __ldg(&edges[e_next]);
             if (n + 2 * CTA_THREADS < M) e_next = __ldcs(&perm[n + 2 * CTA_THREADS]);
+            // a batch takes at most CTA_THREADS rounds: rebase the claim epoch long before it
+            // can run out (graphs with millions of merging rounds per run)
+            if (epoch < EPOCH_LOW) {
+                __syncthreads();
+                for (int i = tid; i < (1 << clog); i += CTA_THREADS) claim[i] = CLAIM_FREE;
+                if (tid == 0) sh->star_epoch = 0xffffffffu;
+                epoch = a.epoch_start;
+                __syncthreads();
+            }
 
             uint32_t ru = 0, rv = 0, tu = 0, tv = 0;
 #ifdef PZ_TIMING
@@ -583,8 +595,13 @@ __global__ void __launch_bounds__(32 * CTA_WARPS, 1) sweep_cta_kernel(SweepArgs 
                     // star bonds merge together iff no earlier bond of the batch is blocked
                     const bool sw = own && star && (uint32_t)tid < sh->bmin;
                     unsigned long long v = 0ull, incl = 0ull;
+                    // the hub's side bits as of the start of the round: read BEFORE the barrier
+                    // below, behind which the first star bond publishes the whole round's bits
+                    // (StoreS16 keeps them in a live shared-memory word, not in the token)
+                    uint32_t hs = 0u;
                     if (__any_sync(0xffffffffu, sw)) {
                         const uint32_t so = sw ? st.sides_of_root(o, to) : 0u;
+                        if (sw && track) hs = st.sides_of_root(hub, th);
                         v = sw ? ((unsigned long long)(Store::size_m1(to) + 1) |
                                   ((unsigned long long)(so & 1u) << 40) |
                                   ((unsigned long long)(so >> 1) << 50)) : 0ull;
@@ -610,7 +627,6 @@ __global__ void __launch_bounds__(32 * CTA_WARPS, 1) sweep_cta_kernel(SweepArgs 
                         rec = make_rec<Rec>(Store::size_m1(to), hub_m1 + pre_sz);
                         st.make_child(o, hub);
                         if (track) {
-                            const uint32_t hs = st.sides_of_root(hub, th);
                             const unsigned long long in = pre + v;
                             const uint32_t m = hs | (((in >> 40) & 0x3ffu) ? 1u : 0u) |
                                                (((in >> 50) & 0x3ffu) ? 2u : 0u);
@@ -879,7 +895,7 @@ __global__ void __launch_bounds__(FW_ALL + 256, 1) sweep_fw_kernel(SweepArgs a, 
             // ---- main warps: rounds -----------------------------------------------------------
             Rec *rec_out = reinterpret_cast<Rec *>(a.recs) + (size_t)run * M;
             bool track = spanning;                 // uniform over the main warps
-            uint32_t epoch = 0x003fffffu;          // decreasing: newer claims always win over stale ones
+            uint32_t epoch = a.epoch_start;        // decreasing: newer claims always win over stale ones
             if (nb > 0) nb_arrive(3, FW_ALL);      // the buffer is free
 #ifdef PZ_TIMING
             long long fw_wait = 0, fw_walk = 0, fw_tail = 0, fw_ntail = 0, fw_trounds = 0, fw_cta = 0, fw_ncta = 0, fw_titems = 0;
@@ -888,6 +904,13 @@ __global__ void __launch_bounds__(FW_ALL + 256, 1) sweep_fw_kernel(SweepArgs a, 
             for (int b = 0; b < nb; ++b) {
                 const int n = b * FW_MAIN + tid;   // bond index; row index is n + 1
                 const bool valid = n < M;
+                if (epoch < EPOCH_LOW) {           // rebase the claim epoch (see sweep_cta_kernel)
+                    nb_sync(1, FW_MAIN);
+                    for (int i = tid; i < (int)claim_n; i += FW_MAIN) claim[i] = CLAIM_FREE;
+                    if (tid == 0) sh->star_epoch = 0xffffffffu;
+                    epoch = a.epoch_start;
+                    nb_sync(1, FW_MAIN);
+                }
 #ifdef PZ_TIMING
                 const long long tw0 = clock64();
 #endif

@@ -104,11 +104,11 @@ def _run_rows(lowered, seeds, device=None, rng='mt19937'):
     """Rows of the runs seeded by ``seeds`` (shape (R, M+1))."""
     ctx = _native.context_for(lowered, _default_device() if device is None else device)
     seeds = list(seeds)
-    if rng in ('philox', 'feistel'):
+    if rng not in _native.RNG_MODES:
+        raise ValueError("rng must be one of %s" % sorted(_native.RNG_MODES))
+    if rng != 'mt19937':
         return ctx.run_rows(len(seeds), _native.RNG_MODES[rng],
                             np.asarray(seeds, dtype=np.uint32))
-    if rng != 'mt19937':
-        raise ValueError("rng must be 'mt19937', 'philox' or 'feistel'")
     if all(_is_u32_seed(s) for s in seeds):
         # numpy's legacy stream reproduced on the device, bit for bit
         return ctx.run_rows(len(seeds), _native.PERM_MT19937,
@@ -439,7 +439,7 @@ def bond_canonical_averages_batch(
     ctx.set_ps(np.asarray(ps, dtype=np.float64))
     ctx.reset_accumulators()
     if rng not in _native.RNG_MODES:
-        raise ValueError("rng must be 'mt19937', 'philox' or 'feistel'")
+        raise ValueError("rng must be one of %s" % sorted(_native.RNG_MODES))
     ctx.run_fused(seeds.size, _native.RNG_MODES[rng], seeds, _native.FUSE_CANON)
     if kwargs.get('distributed'):
         # ``seeds`` is this rank's shard: fold the partials of all ranks (rank order)
@@ -483,7 +483,7 @@ def bond_statistics_batch(
     ctx = _native.context_for(lowered, _default_device() if device is None else device)
     rng = kwargs.get('rng', 'philox')
     if rng not in _native.RNG_MODES:
-        raise ValueError("rng must be 'mt19937', 'philox' or 'feistel'")
+        raise ValueError("rng must be one of %s" % sorted(_native.RNG_MODES))
     mode = _native.RNG_MODES[rng]
     seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
     ps = np.ascontiguousarray(ps, dtype=np.float64)

@@ -47,11 +47,29 @@ class LoweredGraph(object):
         self.side_mask = side_mask
         self.preconnected = bool(preconnected)
         self.node_labels = node_labels      # list of original node objects or None
+        self.lattice = None                 # ('grid2d' | 'grid3d', L): labels in closed form
         self._handles = {}                  # device id -> native handle (set by _native)
+
+    # device contexts hold ctypes pointers: they never travel with a copy or a pickle
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state['_handles'] = {}
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._handles = {}
 
     # -- networkx-like surface ------------------------------------------------
     def label(self, i):
-        return i if self.node_labels is None else self.node_labels[i]
+        if self.node_labels is not None:
+            return self.node_labels[i]
+        if self.lattice is not None:
+            kind, L = self.lattice
+            if kind == 'grid2d':
+                return (i // L + 1, i % L)
+            return (i // (L * L), (i // L) % L, i % L)
+        return i
 
     def edges(self):
         return [(self.label(int(u)), self.label(int(v)))
@@ -71,8 +89,20 @@ class LoweredGraph(object):
         return self.num_edges
 
     def without_spanning(self):
-        return LoweredGraph(self.num_nodes, self.eu, self.ev, None, False,
-                            self.node_labels)
+        g = LoweredGraph(self.num_nodes, self.eu, self.ev, None, False,
+                         self.node_labels)
+        g.lattice = self.lattice
+        return g
+
+    def fingerprint(self):
+        """Content hash of everything the kernels consume."""
+        import hashlib
+        h = hashlib.blake2b(digest_size=16)
+        h.update(np.int64([self.num_nodes, self.num_edges, int(self.preconnected)]).tobytes())
+        h.update(self.eu.tobytes())
+        h.update(self.ev.tobytes())
+        h.update(b'-' if self.side_mask is None else self.side_mask.tobytes())
+        return h.hexdigest()
 
 
 class _HostUnionFind(object):
@@ -95,7 +125,22 @@ class _HostUnionFind(object):
             self.parent[self.find(x)] = r
 
 
-_LOWER_CACHE_ATTR = "_pz_lowered"
+# Lowered forms of graphs seen before: a side table keyed weakly by the graph object (the caller's
+# object is never written to, so it still pickles and deep-copies), validated by a fingerprint of
+# everything the lowering reads -- a graph mutated in place (a rewired bond, a changed 'span'
+# attribute) is lowered again.
+import weakref
+
+_LOWER_CACHE = weakref.WeakKeyDictionary()
+
+
+def _graph_fingerprint(perc_graph, spanning_cluster, auxiliary_node_attributes,
+                       auxiliary_edge_attributes, spanning_sides):
+    def attr_items(d):
+        return None if d is None else tuple(d.items())
+    return hash((bool(spanning_cluster), tuple(perc_graph.nodes()), tuple(perc_graph.edges()),
+                 attr_items(auxiliary_node_attributes), attr_items(auxiliary_edge_attributes),
+                 None if spanning_sides is None else tuple(spanning_sides)))
 
 
 def lower(perc_graph, spanning_cluster=True, auxiliary_node_attributes=None,
@@ -124,13 +169,14 @@ def lower(perc_graph, spanning_cluster=True, auxiliary_node_attributes=None,
                 'of less or more than 2 types (sides) given.'
             )
 
-    cache = getattr(perc_graph, "__dict__", {}).get(_LOWER_CACHE_ATTR)
-    key = (bool(spanning_cluster), id(auxiliary_node_attributes),
-           id(auxiliary_edge_attributes))
-    if cache is not None and cache[0] == key and \
-            cache[1].num_edges == perc_graph.number_of_edges() and \
-            cache[1].num_nodes == perc_graph.number_of_nodes():
-        return cache[1]
+    try:
+        key = _graph_fingerprint(perc_graph, spanning_cluster, auxiliary_node_attributes,
+                                 auxiliary_edge_attributes, spanning_sides)
+        cached = _LOWER_CACHE.get(perc_graph)
+    except TypeError:                      # unhashable node objects / not weak-referenceable
+        key, cached = None, None
+    if cached is not None and cached[0] == key:
+        return cached[1]
 
     nodes = list(perc_graph.nodes())
     index = {node: i for i, node in enumerate(nodes)}
@@ -170,10 +216,11 @@ def lower(perc_graph, spanning_cluster=True, auxiliary_node_attributes=None,
             side_mask[m[1]] = (1 if r == roots[0] else 0) | (2 if r == roots[1] else 0)
 
     lowered = LoweredGraph(len(nodes), eu, ev, side_mask, preconnected, nodes)
-    try:
-        perc_graph.__dict__[_LOWER_CACHE_ATTR] = (key, lowered)
-    except (AttributeError, TypeError):
-        pass
+    if key is not None:
+        try:
+            _LOWER_CACHE[perc_graph] = (key, lowered)
+        except TypeError:
+            pass
     return lowered
 
 
@@ -203,7 +250,7 @@ def lowered_spanning_2d_grid(length):
     labels = [(i + 1, j) for i in range(L) for j in range(L)] if L <= 64 else None
     g = LoweredGraph(L * L, src[keep], tgt[keep], side_mask, False, labels)
     if labels is None:
-        g.label = lambda k, L=L: (k // L + 1, k % L)
+        g.lattice = ('grid2d', L)
     return g
 
 
@@ -236,5 +283,5 @@ def lowered_spanning_3d_grid(length):
     side_mask[ids[0].reshape(-1)] |= 1
     side_mask[ids[-1].reshape(-1)] |= 2
     g = LoweredGraph(L ** 3, src[keep], tgt[keep], side_mask, False, None)
-    g.label = lambda k, L=L: (k // (L * L), (k // L) % L, k % L)
+    g.lattice = ('grid3d', L)
     return g

@@ -78,25 +78,87 @@ def allgather_merge_canon(count, mean, m2, group=None, device=None):
     return c, mu, s2
 
 
-def allreduce_context(ctx, group=None):
-    """Combine the accumulators of every rank's context (device-resident
-    exchange over NCCL).  After the call every rank holds the totals."""
+def exchange_comm_id_file(path, rank, timeout=300.0):
+    """Hand rank 0's communicator id to the other ranks through a file on a shared file system
+    (the transport the reference's Jug workers use for everything): rank 0 writes ``path``
+    atomically, the others wait for it.  No torch, no MPI."""
+    import os
+    import time
+    from . import _native
+    if rank == 0:
+        comm_id = _native.comm_unique_id()
+        tmp = "%s.tmp.%d" % (path, os.getpid())
+        with open(tmp, "wb") as f:
+            f.write(comm_id)
+        os.replace(tmp, path)
+        return comm_id
+    t0 = time.time()
+    while True:
+        try:
+            with open(path, "rb") as f:
+                comm_id = f.read()
+            if len(comm_id) == _native.COMM_ID_BYTES:
+                return comm_id
+        except IOError:
+            pass
+        if time.time() - t0 > timeout:
+            raise RuntimeError("no communicator id at %r after %.0f s" % (path, timeout))
+        time.sleep(0.01)
+
+
+def exchange_comm_id_torch(group=None, device=None):
+    """The same through an initialised ``torch.distributed`` group (any backend)."""
     import torch
     import torch.distributed as dist
-    dev = torch.device("cuda", ctx.device)
-    runs = torch.tensor([ctx.micro_runs], dtype=torch.int64, device=dev)
+    from . import _native
+    rank = dist.get_rank(group)
+    raw = _native.comm_unique_id() if rank == 0 else bytes(_native.COMM_ID_BYTES)
+    t = torch.tensor(list(raw), dtype=torch.uint8)
+    if dist.get_backend(group) == "nccl":
+        t = t.to(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
+    src = dist.get_global_rank(group, 0) if group is not None else 0
+    dist.broadcast(t, src=src, group=group)
+    return bytes(t.cpu().tolist())
+
+
+def ensure_comm(ctx, group=None):
+    """Give ``ctx`` a communicator over the ranks of ``group`` (once per context)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if ctx.comm_world != world:
+        comm_id = exchange_comm_id_torch(group, torch.device("cuda", ctx.device))
+        ctx.comm_init(world, dist.get_rank(group), comm_id)
+    return ctx
+
+
+def allreduce_context(ctx, group=None):
+    """Combine the accumulators of every rank's context; afterwards every rank holds the totals.
+
+    One collective step through the C-ABI (``pz_allreduce``: NCCL integer all-reduce of the micro
+    accumulators with the run count, all-gather + rank-ordered Chan merge of the canonical
+    partials) on the context's own stream.  ``torch.distributed`` only carries the communicator
+    id to the ranks the first time.  With a non-NCCL backend (gloo in the CPU tests of the host
+    logic) the same exchange is made through host arrays."""
+    import torch.distributed as dist
+    if dist.get_backend(group) == "nccl":
+        ensure_comm(ctx, group).allreduce()
+        return ctx.micro_runs
+    return _allreduce_context_host(ctx, group)
+
+
+def _allreduce_context_host(ctx, group=None):
+    """``allreduce_context`` for backends that move host memory (gloo)."""
+    import torch
+    import torch.distributed as dist
+    runs = torch.tensor([ctx.micro_runs], dtype=torch.int64)
     dist.all_reduce(runs, op=dist.ReduceOp.SUM, group=group)
     total_runs = int(runs.item())
     if total_runs > 0:
-        from . import _native
-        words = torch.empty(((ctx.M + 1) * _native.ACC_WORDS,), dtype=torch.int64, device=dev)
-        ctx.micro_export(device_ptr=words.data_ptr())
-        torch.cuda.current_stream(dev).synchronize()
-        dist.all_reduce(words, op=dist.ReduceOp.SUM, group=group)
-        torch.cuda.current_stream(dev).synchronize()
-        ctx.micro_import(words.data_ptr(), total_runs, is_device=True)
+        words = allreduce_words(ctx.micro_export(), group=group)
+        ctx.micro_import(words, total_runs)
     if ctx.num_p:
         count, mean, m2 = ctx.canon_export()
-        c, mu, s2 = allgather_merge_canon(count, mean, m2, group=group, device=dev)
+        c, mu, s2 = allgather_merge_canon(count, mean, m2, group=group)
         ctx.canon_replace(c, mu, s2)
     return total_runs

@@ -70,18 +70,27 @@ def percolation_graph(graph, spanning_cluster=True):
     return out
 
 
-_GRAPH_CACHE_ATTR = '_pz_percolation'
+# lowered forms of user graphs, keyed weakly by the graph object and validated by a fingerprint
+# of its nodes, bonds and 'span' attributes (see lowering._LOWER_CACHE); the user's graph is
+# never written to
+import weakref
+
+_PREPARED = weakref.WeakKeyDictionary()
 
 
 def _prepare(graph, spanning_cluster):
-    """(LoweredGraph, list of bonds as node pairs) for ``graph``."""
+    """LoweredGraph for ``graph`` (a networkx graph with auxiliary nodes, or a LoweredGraph)."""
     if isinstance(graph, _lowering.LoweredGraph):
         return _lowering.lower(graph, spanning_cluster=spanning_cluster)
-    cache = getattr(graph, '__dict__', {}).get(_GRAPH_CACHE_ATTR)
-    key = (bool(spanning_cluster), graph.number_of_nodes(),
-           graph.number_of_edges())
-    if cache is not None and cache[0] == key:
-        return cache[1]
+    try:
+        key = hash((bool(spanning_cluster), tuple(graph.nodes()), tuple(graph.edges()),
+                    tuple(nx.get_node_attributes(graph, 'span').items()),
+                    tuple(nx.get_edge_attributes(graph, 'span').items())))
+        cached = _PREPARED.get(graph)
+    except TypeError:
+        key, cached = None, None
+    if cached is not None and cached[0] == key:
+        return cached[1]
     pg = percolation_graph(graph, spanning_cluster=spanning_cluster)
     lowered = _lowering.lower(
         pg['perc_graph'], spanning_cluster=spanning_cluster,
@@ -89,10 +98,11 @@ def _prepare(graph, spanning_cluster):
         auxiliary_edge_attributes=pg.get('auxiliary_edge_attributes'),
         spanning_sides=pg.get('spanning_sides'),
     )
-    try:
-        graph.__dict__[_GRAPH_CACHE_ATTR] = (key, lowered)
-    except (AttributeError, TypeError):
-        pass
+    if key is not None:
+        try:
+            _PREPARED[graph] = (key, lowered)
+        except TypeError:
+            pass
     return lowered
 
 

@@ -111,18 +111,16 @@ def finite_size_study(system_dimensions=(8, 16, 32), number_of_runs=10000,
     for L in system_dimensions:
         L = int(L)
         g = graph(L)
-        if isinstance(g, dict):
-            kwargs = dict(g)
-            lowered_nodes = kwargs['num_nodes']
+        if isinstance(g, lowering.LoweredGraph):
+            kwargs = dict(perc_graph=g, num_nodes=g.num_nodes, num_edges=g.num_edges)
         else:
-            if not isinstance(g, lowering.LoweredGraph):
+            if not isinstance(g, dict):          # a networkx graph with auxiliary nodes
                 from . import percolate as _percolate
                 g = _percolate.percolation_graph(g, spanning_cluster=spanning_cluster)
-                kwargs = dict(g)
-                lowered_nodes = kwargs['num_nodes']
-            else:
-                kwargs = dict(perc_graph=g, num_nodes=g.num_nodes, num_edges=g.num_edges)
-                lowered_nodes = g.num_nodes
+            # a percolation_graph() dict carries its own 'graph' and 'spanning_cluster' entries
+            # (percolate/percolate.py:55-100); the study's spanning_cluster argument decides
+            kwargs = {k: v for k, v in g.items() if k not in ('graph', 'spanning_cluster')}
+        lowered_nodes = kwargs['num_nodes']
         my = seeds[L]
         if world > 1:
             from . import multi

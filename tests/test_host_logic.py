@@ -340,3 +340,37 @@ def test_host_helpers_against_the_live_reference():
                     assert list(pa[key].nodes()) == list(pb[key].nodes())
                 else:
                     assert pa[key] == pb[key], key
+
+
+def test_study_accepts_every_documented_graph_callable(monkeypatch):
+    """finite_size_study(graph=...) takes a LoweredGraph, a networkx graph with auxiliary nodes or a
+    percolation_graph dict; none of them may collide with the study's own keyword arguments."""
+    from pypercolate_b200 import hpc, study, percolate, lowering
+    seen = []
+
+    def fake_batch(**kwargs):
+        seen.append(kwargs)
+        ps = kwargs['ps']
+        out = np.zeros(ps.size, dtype=hpc.canonical_averages_dtype(kwargs['spanning_cluster']))
+        out['number_of_runs'] = kwargs['seeds'].size
+        return out
+
+    monkeypatch.setattr(hpc, 'bond_canonical_averages_batch', fake_batch)
+    kinds = {
+        'lowered': lowering.lowered_spanning_2d_grid,
+        'networkx': percolate.spanning_2d_grid,
+        'dict': lambda L: percolate.percolation_graph(percolate.spanning_2d_grid(L)),
+    }
+    for name, fn in kinds.items():
+        for spanning in (True, False):
+            seen.clear()
+            res = study.finite_size_study(system_dimensions=(3,), number_of_runs=5,
+                                          ps=np.linspace(0.3, 0.7, 4), graph=fn,
+                                          spanning_cluster=spanning)
+            assert set(res) == {3} and res[3]['number_of_runs'].tolist() == [5] * 4
+            kw = seen[0]
+            # (like the reference's percolation_graph, a networkx graph keeps its auxiliary nodes
+            # when no spanning cluster is to be detected, percolate/percolate.py:55-100)
+            whole = name == 'networkx' and not spanning
+            assert (kw['num_nodes'], kw['num_edges']) == ((15, 22) if whole else (9, 12)), name
+            assert kw['spanning_cluster'] is spanning and 'graph' not in kw

@@ -107,3 +107,59 @@ def test_preconnected_detection():
     h.add_edge('a', 'b', span=0)
     low, _ = lower_graph(h)
     assert low.preconnected
+
+
+# -- caches and copies (the user's graph object is never written to) -------------
+
+def test_lowering_follows_in_place_mutation_of_the_graph():
+    g = percolate.spanning_2d_grid(4)
+    a = percolate._prepare(g, True)
+    assert percolate._prepare(g, True) is a                       # unchanged graph: cached
+    # rewire one bond, same node and bond counts
+    g.remove_edge((1, 0), (1, 1))
+    g.add_edge((1, 0), (3, 3))
+    b = percolate._prepare(g, True)
+    assert b is not a and b.num_edges == a.num_edges
+    assert b.fingerprint() != a.fingerprint()
+    assert ((1, 0), (3, 3)) in b.edges() and ((1, 0), (1, 1)) not in b.edges()
+    # move an auxiliary bond to the other side: same counts again
+    edge = next(e for e, s in nx.get_edge_attributes(g, 'span').items() if s == 0)
+    g.edges[edge]['span'] = 1
+    c = percolate._prepare(g, True)
+    assert c is not b and not np.array_equal(c.side_mask, b.side_mask)
+
+
+def test_lower_cache_keyed_by_content_not_identity():
+    pg = percolate.percolation_graph(percolate.spanning_2d_grid(3))
+    args = (pg['perc_graph'], True, pg['auxiliary_node_attributes'],
+            pg['auxiliary_edge_attributes'], pg['spanning_sides'])
+    a = lowering.lower(*args)
+    assert lowering.lower(*args) is a
+    # equal content in fresh dict objects still hits; changed content does not
+    assert lowering.lower(args[0], True, dict(args[2]), dict(args[3]), list(args[4])) is a
+    flipped = {e: 1 - s for e, s in args[3].items()}
+    b = lowering.lower(args[0], True, args[2], flipped, args[4])
+    # (the auxiliary nodes keep their side, their bonds now carry the other one: both hubs merge)
+    assert b is not a and b.preconnected and not a.preconnected
+
+
+def test_graphs_still_pickle_and_deepcopy_after_lowering():
+    import copy
+    import pickle
+    g = percolate.spanning_2d_grid(3)
+    low = percolate._prepare(g, True)
+    low._handles[0] = object()              # stands in for a ctypes device context
+    assert '_pz_percolation' not in g.__dict__ and '_pz_lowered' not in g.__dict__
+    g2 = pickle.loads(pickle.dumps(g))
+    assert sorted(g2.edges()) == sorted(g.edges())
+    copy.deepcopy(g)
+    pg = percolate.percolation_graph(g)
+    lowering.lower(pg['perc_graph'], True, pg['auxiliary_node_attributes'],
+                   pg['auxiliary_edge_attributes'], pg['spanning_sides'])
+    copy.deepcopy(pg)
+    for big in (low, lowering.lowered_spanning_2d_grid(70), lowering.lowered_spanning_3d_grid(5)):
+        big._handles[0] = object()
+        for clone in (pickle.loads(pickle.dumps(big)), copy.deepcopy(big)):
+            assert clone._handles == {} and clone.fingerprint() == big.fingerprint()
+            assert clone.label(clone.num_nodes - 1) == big.label(big.num_nodes - 1)
+            assert clone.edges()[:5] == big.edges()[:5]
