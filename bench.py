@@ -8,12 +8,16 @@ L = 256 square lattice (BASELINE.json config 3: 1e5 runs, fused microcanonical
     python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm
 
 A step is one pass of the hot path over the whole batch of runs: bond orders
-(device RNG: the Philox-keyed Feistel bijection by default, `--rng philox` for the
-bucketed Philox Fisher-Yates) -> union-find sweep -> per-n exact sums over runs and
-per-run binomial contraction -> (multi-GPU) one NCCL exchange -> per-n mean /
-variance.  Strong scaling: the 1e5 runs are split over the ranks.
+(device RNG, `--rng`: numpy's MT19937 stream bit for bit, Philox Fisher-Yates, the
+bucketed Philox shuffle or the Philox-keyed Feistel bijection) -> union-find sweep ->
+per-n exact sums over runs and per-run binomial contraction -> (multi-GPU) one NCCL
+exchange -> per-n mean / variance.  Strong scaling: the 1e5 runs are split over the ranks.
 
-One JSON line is printed by rank 0 (see the driver contract in the task text).
+One JSON line is printed by rank 0 (see the driver contract in the task text).  Besides the
+headline (BASELINE config 3) it carries, under "configs", one short measurement of the other
+GPU configs of BASELINE.json (c2, c4, c5, sharded over the same N GPUs) and of config 3 under
+the other generators, under "multi_gpu_parity" (N > 1) the comparison of a sharded job with the
+same job on one rank, and under "e2e" the cold first call next to the warm figure.
 """
 import argparse
 import json
@@ -43,10 +47,14 @@ RNG_TEXT = {
     "feistel": "bond orders on device = Philox-keyed 20-round Feistel bijection with cycle walking",
     "philox": "bond orders on device = Philox4x32-10 bucketed Fisher-Yates",
     "mt19937": "bond orders on device = numpy RandomState(seed).permutation stream, bit for bit",
+    "philox_fy": "bond orders on device = textbook Fisher-Yates with Philox4x32-10 counter-based draws",
 }
 
 
-def workload_config(n_gpus, runs_total, rng="feistel"):
+DEFAULT_RNG = "mt19937"
+
+
+def workload_config(n_gpus, runs_total, rng=DEFAULT_RNG):
     return {
         "workload": "spanning_2d_grid L=256 (N=65536, M=130560), %d runs total, %s, "
                     "fused microcanonical sums + per-run canonical contraction at "
@@ -120,24 +128,39 @@ class ClockSampler(object):
         return out
 
 
-def cpu_port_rate(seconds_target, threads=None):
-    """The oracle port (oracle/pz_oracle.c: reference semantics, rows
-    materialised, numpy-stream permutation inside) on the host cores."""
+def cpu_fused_rate(seconds_target):
+    """The reference's algorithm on the host cores: the oracle port (oracle/pz_oracle.c) of the
+    WHOLE fused job of config 3 -- numpy-stream permutation, sweep, per-n sums over runs, per-run
+    binomial contraction at 100 p folded into (count, mean, M2) -- OpenMP over every host thread.
+    The thread count is set explicitly (a multi-process launcher pre-sets OMP_NUM_THREADS=1) and
+    the count OpenMP really used is what is reported."""
     from oracle import oracle
     from pypercolate_b200 import lowering
     g = lowering.lowered_spanning_2d_grid(L)
-    cores = threads or os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    warm = np.arange(cores, dtype=np.uint32) + 1
+    want = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    threads = oracle.set_threads(want)
+    global _CPU_TABLES
+    if _CPU_TABLES is None:      # binomial weights: built once, like pz_set_ps keeps them on the GPU
+        _CPU_TABLES = oracle.fused_tables(g.num_edges, np.linspace(0.45, 0.55, NUM_P))
+    ps = _CPU_TABLES
+    warm = np.arange(threads, dtype=np.uint32) + 1
     t0 = time.perf_counter()
-    oracle.sweep_many_checksums(g.num_nodes, g.num_edges, g.eu, g.ev, g.side_mask, False, warm)
+    oracle.fused_many(g.num_nodes, g.num_edges, g.eu, g.ev, g.side_mask, False, warm, ps)
     per_wave = max(time.perf_counter() - t0, 1e-3)
     waves = max(1, int(seconds_target / per_wave))
-    seeds = np.arange(cores * waves, dtype=np.uint32) + 1000
+    seeds = np.arange(threads * waves, dtype=np.uint32) + 1000
     t0 = time.perf_counter()
-    oracle.sweep_many_checksums(g.num_nodes, g.num_edges, g.eu, g.ev, g.side_mask, False, seeds)
+    micro, mean, m2 = oracle.fused_many(g.num_nodes, g.num_edges, g.eu, g.ev, g.side_mask, False, seeds, ps)
     dt = time.perf_counter() - t0
-    return seeds.size * g.num_edges / dt, cores, seeds.size, dt
+    assert micro[1, -1] == float(seeds.size) * g.num_nodes        # every run ends in one cluster
+    return seeds.size * g.num_edges / dt, threads, seeds.size, dt
+
+
+_CPU_TABLES = None
+CPU_SAMPLE_TEXT = ("%d runs of L=256 in %.1f s: numpy-stream permutation + sweep + per-n sums over runs + "
+                   "per-run binomial contraction at 100 p folded into (count, mean, M2); C port of the "
+                   "reference's algorithm (oracle/pz_oracle.c), OpenMP over %d threads (measured: "
+                   "omp_get_num_threads inside a parallel region)")
 
 
 def run_reference(args, rank, world):
@@ -147,25 +170,27 @@ def run_reference(args, rank, world):
     per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
     cores = runs = 0
     for i in range(args.warmup + args.steps):
-        rate, cores, runs, dt = cpu_port_rate(per_step)
+        rate, cores, runs, dt = cpu_fused_rate(per_step)
         if i >= args.warmup:
             vals.append((rate, dt))
     value = float(np.mean([v for v, _ in vals]))
-    sample = ("%d runs of L=256 per step (permutation via the numpy MT19937 stream + sweep + "
-              "53-byte rows), OpenMP over %d threads" % (runs, cores))
+    dt = float(np.mean([d for _, d in vals]))
+    config = workload_config(args.gpus, TOTAL_RUNS, "mt19937")
+    config["timed_sample"] = ("each step times %d runs of this workload (same lattice, same generator, "
+                              "same statistics) on %d host threads; bond-additions/s does not depend on "
+                              "the number of runs (independent units)" % (runs, cores))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": float(np.mean([d for _, d in vals]) * 1e3), "higher_is_better": True,
+        "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": workload_config(args.gpus, TOTAL_RUNS),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": config,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": CPU_SAMPLE_TEXT % (runs, dt, cores)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference is pure Python (~4e4 bond-additions/s per core, BASELINE.md) and "
                 "cannot travel to the GPU box; this arm times the C restatement of its algorithm "
-                "(oracle/pz_oracle.c) on all host cores.  It materialises the rows of every run "
-                "(bond_microcanonical_statistics) but does NOT average them or contract them with the "
-                "binomial weights, i.e. it does less work per run than the GPU arm",
+                "(oracle/pz_oracle.c) doing the same job as the GPU arm, on all host threads",
     }
     emit(line)
 
@@ -180,6 +205,19 @@ _REAL_STDOUT = os.dup(1)
 os.dup2(2, 1)
 
 
+SECONDARY = [
+    # name, lattice, L, total runs, (p_lo, p_hi, num_p), flags, rng, what BASELINE.json says
+    ("c2", "2d", 128, 10 ** 4, (0.4, 0.6, 40), "canon", None,
+     "spanning_2d_grid L=128, 1e4 runs, per-run statistics reduced with bond_reduce at the jugfile's 40 p "
+     "(parent array in shared memory)"),
+    ("c4", "2d", 1024, 10 ** 3, (0.45, 0.55, 100), "both", None,
+     "spanning_2d_grid L=1024, 1e3 runs, fused microcanonical + canonical averaging (global-memory store)"),
+    ("c5", "3d", 64, 10 ** 4, (0.2, 0.3, 100), "both", None,
+     "simple-cubic L=64 as a general edge list with top/bottom sides, 1e4 runs, fused microcanonical + "
+     "canonical averaging (global-memory store)"),
+]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -188,7 +226,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--runs", type=int, default=TOTAL_RUNS, help="total runs per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--rng", default="feistel", choices=["feistel", "philox", "mt19937"],
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the short measurements of the other configs / generators")
+    ap.add_argument("--rng", default=DEFAULT_RNG, choices=sorted(RNG_TEXT),
                     help="device bond-order generator of our arm")
     args = ap.parse_args()
 
@@ -217,17 +257,41 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def seeds_of(lo, hi):
+        return (np.arange(lo, hi, dtype=np.uint64) * 2654435761 % (2 ** 32)).astype(np.uint32)
+
     g = lowering.lowered_spanning_2d_grid(L)
     M, N = g.num_edges, g.num_nodes
-    ctx = _native.context_for(g, local)
+    ctx = _native.context_for(g, local)           # CUDA context + graph upload: not part of any timing
     ps = np.linspace(0.45, 0.55, NUM_P)
-    ctx.set_ps(ps)
     lo, hi = multi.shard_bounds(args.runs, rank, world)
     my_runs = hi - lo
-    seeds_host = (np.arange(lo, hi, dtype=np.uint64) * 2654435761 % (2 ** 32)).astype(np.uint32)
-    seeds_dev = torch.from_numpy(seeds_host.view(np.int32)).cuda()
+    seeds_host = seeds_of(lo, hi)
     flags = _native.FUSE_MICRO | _native.FUSE_CANON
     mode = _native.RNG_MODES[args.rng] | _native.SEEDS_ON_DEVICE
+
+    def step_e2e():
+        """the public call: host seeds / ps in, host statistics out"""
+        return hpc.bond_statistics_batch(g, N, M, seeds_host, ps, 0.3173, device=local,
+                                         rng=args.rng, distributed=world > 1)
+
+    # ---- the first call of a study: nothing cached (binomial table, beta-interval table, scratch
+    # buffers, NCCL communicator) ---------------------------------------------------------------
+    barrier()
+    t0 = time.perf_counter()
+    step_e2e()
+    barrier()
+    e2e_cold_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+
+    seeds_dev = torch.from_numpy(seeds_host.view(np.int32)).cuda()
+    ctx.set_ps(ps)
 
     def step_device():
         """inputs (graph, seeds, binomial weights) resident in HBM"""
@@ -236,11 +300,6 @@ def main():
         if world > 1:
             multi.allreduce_context(ctx)
         ctx.micro_finalize_device_only()
-
-    def step_e2e():
-        """the public call: host seeds / ps in, host statistics out"""
-        return hpc.bond_statistics_batch(g, N, M, seeds_host, ps, 0.3173, device=local,
-                                         rng=args.rng, distributed=world > 1)
 
     # ---- device-resident throughput -------------------------------------------
     for _ in range(args.warmup):
@@ -259,8 +318,7 @@ def main():
     ctx.profile(False)
     clocks = sampler.stop() if sampler else None
 
-    # ---- end to end through the public API ---------------------------------------
-    step_e2e()
+    # ---- end to end through the public API (warm: tables of the first call are kept) ----------
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -277,6 +335,90 @@ def main():
         ms, e2e_ms, launches = float(tmax[0]), float(tmax[1]), int(tsum[2])
     else:
         e2e_ms = e2e_s * 1e3
+    assert res["number_of_runs"] == args.runs
+
+    # ---- multi-GPU parity (untimed): a sharded job against the same job on rank 0 alone ---------
+    parity = None
+    if world > 1:
+        pr = 1200
+        plo, phi = multi.shard_bounds(pr, rank, world)
+        ctx.reset_accumulators()
+        ctx.run_fused(phi - plo, _native.RNG_MODES[args.rng], seeds_of(plo, phi), flags)
+        multi.allreduce_context(ctx)
+        sharded_runs = ctx.micro_runs
+        sh_mean, sh_var = ctx.micro_finalize()
+        sh_canon = ctx.canon_export()
+        if rank == 0:
+            ctx.reset_accumulators()
+            ctx.run_fused(pr, _native.RNG_MODES[args.rng], seeds_of(0, pr), flags)
+            one_mean, one_var = ctx.micro_finalize()
+            one_canon = ctx.canon_export()
+            rel = lambda a, b: float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+            parity = {
+                "runs": pr, "ranks": world,
+                "micro_sums_bit_equal": bool(sharded_runs == pr and np.array_equal(sh_mean, one_mean)
+                                             and np.array_equal(sh_var, one_var)),
+                "canonical_count_equal": bool(sh_canon[0] == one_canon[0] == pr),
+                "canonical_mean_max_rel": rel(sh_canon[1], one_canon[1]),
+                "canonical_m2_max_rel": rel(sh_canon[2], one_canon[2]),
+            }
+            parity["ok"] = bool(parity["micro_sums_bit_equal"] and parity["canonical_count_equal"]
+                                and parity["canonical_mean_max_rel"] < 1e-13
+                                and parity["canonical_m2_max_rel"] < 1e-10)
+        barrier()
+
+    # ---- the other configs and generators: one short measurement each --------------------------
+    # (warm-up pass, then one timed pass; same sharding, exchange and finalize as the headline)
+    def close_context(graph):
+        c = graph._handles.pop(local, None)
+        if c is not None:
+            c.close()
+
+    def measure(graph, runs_total, rng, p_range, what):
+        c = _native.context_for(graph, local)
+        fl = {"canon": _native.FUSE_CANON, "both": _native.FUSE_MICRO | _native.FUSE_CANON}[what]
+        c.set_ps(np.linspace(*p_range))
+        a, b = multi.shard_bounds(runs_total, rank, world)
+        sd = torch.from_numpy(seeds_of(a, b).view(np.int32)).cuda()
+        md = _native.RNG_MODES[rng] | _native.SEEDS_ON_DEVICE
+        out = None
+        for timed in (False, True):
+            barrier()
+            c.profile(timed)
+            c.timer_start()
+            c.reset_accumulators()
+            if b > a:
+                c.run_fused(b - a, md, sd.data_ptr(), fl)
+            if world > 1:
+                multi.allreduce_context(c)
+            if fl & _native.FUSE_MICRO:
+                c.micro_finalize_device_only()
+            t_ms = c.timer_stop()
+            barrier()
+            out = max_over_ranks(t_ms)
+        ph = c.profile_read()
+        c.profile(False)
+        bonds = float(runs_total) * graph.num_edges
+        return {"ms": out, "bonds_per_s": bonds / (out * 1e-3), "runs_per_s": runs_total / (out * 1e-3),
+                "runs": runs_total, "rng": rng, "n_gpus": world,
+                "sweep_bonds_per_s_rank0": (float(b - a) * graph.num_edges / (ph["sweep"][0] * 1e-3)
+                                            if ph["sweep"][1] else None)}
+
+    configs = {}
+    if not args.no_secondary:
+        for other in ("mt19937", "philox_fy", "philox", "feistel"):
+            if other == args.rng:
+                continue
+            r = measure(g, args.runs, other, (0.45, 0.55, NUM_P), "both")
+            r["workload"] = "config 3 (the headline workload) with " + RNG_TEXT[other]
+            configs["c3_" + other] = r
+        close_context(g)
+        for name, kind, size, runs_total, p_range, what, rng, text in SECONDARY:
+            graph = (lowering.lowered_spanning_2d_grid if kind == "2d" else lowering.lowered_spanning_3d_grid)(size)
+            r = measure(graph, runs_total, rng or args.rng, p_range, what)
+            r["workload"] = text
+            configs[name] = r
+            close_context(graph)
 
     if rank == 0:
         bonds_per_step = float(args.runs) * M
@@ -314,22 +456,26 @@ def main():
                 "h2d_bytes_per_step": int(seeds_host.nbytes + ps.nbytes),
                 "d2h_bytes_per_step": int(19 * (M + 1) * 8 + 2 * NUM_P * 7 * 8),   # pz_micro_arrays + canonical partials
                 "ms_per_step": e2e_ms / args.steps,
+                "cold_first_call_ms": e2e_cold_ms,
+                "cold_note": "first call in the process: binomial table (100 p), beta-interval table, scratch "
+                             "allocation and (N > 1) the NCCL communicator are built inside it; the warm figure "
+                             "re-uses them, as every later call of a study does",
                 "api": "pypercolate_b200.hpc.bond_statistics_batch (host seeds/ps in, "
                        "microcanonical arrays + finalized canonical averages out)",
             },
             "gpu_launches": launches,
             "clocks": clocks,
+            "configs": configs,
         }
+        if parity is not None:
+            line["multi_gpu_parity"] = parity
         if not args.no_cpu_baseline and world == 1:
-            rate, cores, nruns, dt = cpu_port_rate(12.0)
-            line["cpu_baseline"] = {
-                "value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": "%d runs of L=256 in %.1f s (numpy-stream permutation + sweep + rows), "
-                          "OpenMP over %d threads" % (nruns, dt, cores),
-            }
-        # sanity of the last e2e result (not timed)
-        assert res["number_of_runs"] == args.runs
+            rate, cores, nruns, dt = cpu_fused_rate(12.0)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": CPU_SAMPLE_TEXT % (nruns, dt, cores)}
         emit(line)
+        if parity is not None and not parity["ok"]:
+            raise SystemExit("multi-GPU parity check failed: %r" % (parity,))
     if world > 1:
         dist.destroy_process_group()
 

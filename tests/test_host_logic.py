@@ -374,3 +374,99 @@ def test_study_accepts_every_documented_graph_callable(monkeypatch):
             whole = name == 'networkx' and not spanning
             assert (kw['num_nodes'], kw['num_edges']) == ((15, 22) if whole else (9, 12)), name
             assert kw['spanning_cluster'] is spanning and 'graph' not in kw
+
+
+def test_reference_import_names_resolve_to_this_package():
+    """``import percolate`` / ``import percolate.hpc`` -- what user code and the reference's
+    jugfile (percolate/share/jugfile.py:25-26) say -- bind this package's modules."""
+    import importlib
+    import pypercolate_b200
+    import percolate
+    import percolate.hpc
+    import percolate.percolate
+    assert percolate.hpc is pypercolate_b200.hpc
+    assert percolate.percolate is pypercolate_b200.percolate
+    assert importlib.import_module("percolate.hpc") is pypercolate_b200.hpc
+    for name in ("sample_states", "single_run_arrays", "microcanonical_averages",
+                 "microcanonical_averages_arrays", "canonical_averages", "spanning_1d_chain",
+                 "spanning_2d_grid", "statistics"):
+        assert getattr(percolate, name) is getattr(pypercolate_b200, name)
+    # the names the jugfile reaches for
+    assert callable(percolate.percolate.percolation_graph) and callable(percolate.percolate._binomial_pmf)
+    for name in ("bond_microcanonical_statistics", "bond_canonical_statistics",
+                 "bond_initialize_canonical_averages", "bond_reduce", "finalize_canonical_averages"):
+        assert callable(getattr(percolate.hpc, name))
+
+
+class _FakeH5File(object):
+    """Stand-in for ``h5py.File`` (h5py is not installed in this image): the three members
+    ``study.write_to_disk`` uses -- context manager, ``in``, ``create_dataset`` -- over a pickle."""
+
+    def __init__(self, path, mode='a'):
+        import pickle
+        assert mode == 'a'
+        self.path = path
+        try:
+            with open(path, 'rb') as f:
+                self.data = pickle.load(f)
+        except IOError:
+            self.data = {}
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        import pickle
+        with open(self.path, 'wb') as f:
+            pickle.dump(self.data, f)
+
+    def __contains__(self, key):
+        return key in self.data
+
+    def create_dataset(self, name, data):
+        assert name not in self.data
+        self.data[name] = np.array(data)
+
+
+def test_study_hdf5_branch_with_a_stand_in_h5py(tmp_path, monkeypatch):
+    """The HDF5 output of the study driver (percolate/share/jugfile.py:138-156: one dataset per
+    system size, keyed by the size, an existing key is an error)."""
+    import pickle
+    import sys
+    import types
+    from pypercolate_b200 import hpc, study
+    fake = types.ModuleType('h5py')
+    fake.File = _FakeH5File
+    monkeypatch.setitem(sys.modules, 'h5py', fake)
+    path = str(tmp_path / 'study.h5')
+    rows = np.zeros(3, dtype=hpc.finalized_canonical_averages_dtype(True))
+    rows['p'] = [0.4, 0.5, 0.6]
+    rows['number_of_runs'] = 7
+    study.write_to_disk(path, 16, rows)
+    study.write_to_disk(path, 32, rows)
+    with pytest.raises(RuntimeError):
+        study.write_to_disk(path, 16, rows)
+    with open(path, 'rb') as f:
+        stored = pickle.load(f)
+    assert sorted(stored) == ['16', '32']
+    assert stored['16'].dtype.names == tuple(str(n) for n in rows.dtype.names)
+    assert stored['16']['p'].tolist() == [0.4, 0.5, 0.6] and (stored['32']['number_of_runs'] == 7).all()
+
+
+def test_study_hdf5_branch_with_real_h5py(tmp_path):
+    h5py = pytest.importorskip('h5py', reason="h5py is not installed in this image")
+    from pypercolate_b200 import hpc, study
+    path = str(tmp_path / 'study.h5')
+    rows = np.zeros(2, dtype=hpc.finalized_canonical_averages_dtype(False))
+    study.write_to_disk(path, 8, rows)
+    with h5py.File(path, 'r') as f:
+        assert list(f) == ['8'] and f['8'].shape == (2,)
+
+
+def test_study_hdf5_without_h5py_says_so(tmp_path, monkeypatch):
+    import sys
+    from pypercolate_b200 import hpc, study
+    monkeypatch.setitem(sys.modules, 'h5py', None)          # import h5py -> ImportError
+    with pytest.raises(RuntimeError, match='h5py'):
+        study.write_to_disk(str(tmp_path / 'x.h5'), 8,
+                            np.zeros(1, dtype=hpc.finalized_canonical_averages_dtype(True)))

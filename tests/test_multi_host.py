@@ -73,3 +73,17 @@ def test_gloo_world_size_2(tmp_path):
         np.testing.assert_allclose(r[i]['s2'], ((x - x.mean(axis=0)) ** 2).sum(axis=0), rtol=1e-11)
     # rank-ordered merge: bit-identical on every rank
     assert np.array_equal(r[0]['mu'], r[1]['mu']) and np.array_equal(r[0]['s2'], r[1]['s2'])
+
+
+def test_communicator_id_travels_through_a_file(tmp_path):
+    """The id of the C-ABI's NCCL communicator (pz_comm_unique_id) reaches the other ranks through
+    a file on a shared file system -- no torch needed by a ctypes-only caller."""
+    from pypercolate_b200 import _native
+    path = str(tmp_path / "comm.id")
+    with pytest.raises(RuntimeError):
+        multi.exchange_comm_id_file(path, rank=1, timeout=0.05)      # nothing written yet
+    cid = multi.exchange_comm_id_file(path, rank=0)
+    assert len(cid) == _native.COMM_ID_BYTES
+    assert multi.exchange_comm_id_file(path, rank=1) == cid
+    assert multi.exchange_comm_id_file(path, rank=3) == cid
+    assert _native.comm_unique_id() != cid                            # ids are fresh
