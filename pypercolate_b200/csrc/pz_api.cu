@@ -111,11 +111,6 @@ struct pz_ctx {
     DevBuf<double> pmf;                   // [num_p][M+1], rows in ascending-p order
     DevBuf<int32_t> band_lo, band_hi, tband_lo, tband_hi, porder_dev, canon_flags;
     DevBuf<double> sf;                    // survival functions [num_p][M+1]
-    // thread-per-run generators (MT19937, Philox Fisher-Yates): bond orders of a whole super-chunk of
-    // runs, double buffered -- super-chunk k+1 is generated on s_perm underneath the sweeps of k
-    DevBuf<int32_t> perm_super[2];
-    DevBuf<uint32_t> seed_super[2];
-    cudaEvent_t super_ready[2] = {nullptr, nullptr}, super_free[2] = {nullptr, nullptr};
     DevBuf<uint32_t> validate_bits;       // caller-supplied orders: one bit per (run, bond) + flag word
     int *validate_host = nullptr;         // pinned copy of the flag word
     uint32_t epoch_start = 0x003fffffu;   // first claim epoch of a run (PZ_EPOCH_START: tests)
@@ -209,7 +204,6 @@ cudaError_t launch_perm_feistel(int32_t M, int32_t R, const uint32_t *seeds, int
                                 cudaStream_t s, int *launches);
 cudaError_t launch_perm_philox_fy(int32_t M, int32_t R, const uint32_t *seeds, int32_t *perms,
                                   cudaStream_t s, int *launches);
-int perm_serial_capacity(int sms);
 cudaError_t launch_validate_orders(int32_t M, int32_t R, const int32_t *perms, uint32_t *bitmap,
                                    int *flag, cudaStream_t s);
 }
@@ -262,10 +256,6 @@ int pz_create(int device, pz_ctx **out)
         const long v = atol(e);
         c->epoch_start = (uint32_t)std::min<long>(0x003fffffL, std::max<long>(0x1280L, v));
     }
-    for (int k = 0; k < 2; ++k) {
-        PZ_CUDA(cudaEventCreateWithFlags(&c->super_ready[k], cudaEventDisableTiming));
-        PZ_CUDA(cudaEventCreateWithFlags(&c->super_free[k], cudaEventDisableTiming));
-    }
     PZ_CUDA(cudaMallocHost(&c->validate_host, sizeof(int)));
     {
         size_t free_b = 0, total_b = 0;
@@ -290,11 +280,6 @@ void pz_destroy(pz_ctx *c)
         if (sl.perm_done) cudaEventDestroy(sl.perm_done);
         if (sl.sweep_done) cudaEventDestroy(sl.sweep_done);
         if (sl.stats_done) cudaEventDestroy(sl.stats_done);
-    }
-    for (int k = 0; k < 2; ++k) {
-        c->perm_super[k].release(); c->seed_super[k].release();
-        if (c->super_ready[k]) cudaEventDestroy(c->super_ready[k]);
-        if (c->super_free[k]) cudaEventDestroy(c->super_free[k]);
     }
     c->validate_bits.release();
     if (c->validate_host) cudaFreeHost(c->validate_host);
@@ -672,91 +657,6 @@ int pz_run_fused(pz_ctx *c, int32_t R, int perm_mode, const void *perm_src, int 
         return fail(PZ_ERR_STATE, "pz_run_fused: PZ_FUSE_CANON needs pz_set_ps(M = bonds of the graph) first");
     PZ_CUDA(cudaSetDevice(c->device));
     const int base_mode = perm_mode & ~PZ_SEEDS_ON_DEVICE;
-    if ((base_mode == PZ_PERM_MT19937 || base_mode == PZ_PERM_PHILOX_FY) && R > 0 && c->M > 0) {
-        // Thread-per-run generators: the shuffle is one serial chain per run (a random access per
-        // step), so throughput comes from the number of runs in flight, not from the chunk of the
-        // sweep.  Bond orders are generated a SUPER-CHUNK of runs at a time into one of two
-        // buffers on the bond-order stream; the kernels use no shared memory and few registers,
-        // so super-chunk k+1 is generated on the SMs that sweep super-chunk k (the sweep is bound
-        // by shared-memory latency, the shuffle by random DRAM sectors).  Only the first
-        // super-chunk has nothing to hide behind: it is kept short.
-        const size_t per = (size_t)c->M * 4;
-        const size_t cap = (size_t)perm_serial_capacity(c->sms);        // runs of one co-resident launch
-        size_t super = std::max<size_t>(1, std::min<size_t>(cap, (c->chunk_bytes / 4) / per));
-        if (const char *e = getenv("PZ_SUPER_RUNS")) super = std::max<size_t>(1, (size_t)atoll(e));
-        const bool overlap = c->pipeline != 0;
-        std::vector<size_t> sizes;
-        {
-            // A short first super-chunk (its generation is exposed), then a geometric ramp: the
-            // generation of super-chunk k+1 has to fit under the sweeps and statistics of k, and
-            // it proceeds at roughly 1.5x their pace.  Whole waves of the sweep (multiples of the
-            // SM count).
-            const size_t sms = (size_t)std::max(c->sms, 1);
-            auto waves = [&](size_t x) { return std::max(sms, (x + sms - 1) / sms * sms); };
-            size_t rem = (size_t)R;
-            size_t next = std::min(super, waves(std::max<size_t>(sms * 4, (size_t)R / 16)));
-            if (!overlap) next = super;
-            while (rem > 0) {
-                size_t take = std::min(rem, next);
-                if (rem - take < take / 2) take = rem <= super ? rem : take;   // no short tail
-                sizes.push_back(take);
-                rem -= take;
-                next = std::min(super, waves(next + next / 2));
-            }
-        }
-        cudaStream_t sg = overlap ? c->s_perm : c->stream;
-        auto generate = [&](size_t k, size_t s0) -> int {
-            const int b = (int)(k & 1);
-            const int32_t sn = (int32_t)sizes[k];
-            const uint32_t *seeds_dev = (const uint32_t *)perm_src + s0;
-            if (k >= 2 && overlap) PZ_CUDA(cudaStreamWaitEvent(sg, c->super_free[b], 0));
-            if (!(perm_mode & PZ_SEEDS_ON_DEVICE)) {
-                PZ_CUDA(c->seed_super[b].ensure((size_t)sn));
-                PZ_CUDA(cudaMemcpyAsync(c->seed_super[b].p, (const uint32_t *)perm_src + s0, (size_t)sn * 4,
-                                        cudaMemcpyHostToDevice, sg));
-                seeds_dev = c->seed_super[b].p;
-            }
-            PZ_CUDA(c->perm_super[b].ensure((size_t)sn * c->M));
-            int l = 0;
-            {
-                PhaseTimer t(c, PZ_PHASE_PERM, sg);
-                PZ_CUDA(launch_perm_mode(base_mode, c->M, sn, seeds_dev, c->perm_super[b].p, sg, &l));
-            }
-            c->launches += l;
-            if (overlap) PZ_CUDA(cudaEventRecord(c->super_ready[b], sg));
-            return PZ_OK;
-        };
-        // (buffers are sized before anything is in flight: ensure() may free and reallocate)
-        for (int b = 0; b < 2 && b < (int)sizes.size(); ++b) {
-            size_t need = 0;
-            for (size_t k = b; k < sizes.size(); k += 2) need = std::max(need, sizes[k]);
-            PZ_CUDA(c->perm_super[b].ensure(need * c->M));
-            if (!(perm_mode & PZ_SEEDS_ON_DEVICE)) PZ_CUDA(c->seed_super[b].ensure(need));
-        }
-        PZ_CUDA(cudaStreamSynchronize(c->stream));
-        std::vector<size_t> offs(sizes.size() + 1, 0);
-        for (size_t k = 0; k < sizes.size(); ++k) offs[k + 1] = offs[k] + sizes[k];
-        rc = generate(0, 0); if (rc) return rc;
-        for (size_t k = 0; k < sizes.size(); ++k) {
-            const int b = (int)(k & 1);
-            if (overlap) {
-                PZ_CUDA(cudaStreamWaitEvent(c->stream, c->super_ready[b], 0));
-                // the next super-chunk goes to the bond-order stream BEFORE the sweeps of this one
-                // are launched, so its (few, small) CTAs are resident when the sweep CTAs arrive
-                if (k + 1 < sizes.size()) { rc = generate(k + 1, offs[k + 1]); if (rc) return rc; }
-            }
-            const bool was = c->trusted_orders;
-            c->trusted_orders = true;
-            rc = pz_run_fused(c, (int32_t)sizes[k], PZ_PERM_DEVICE, c->perm_super[b].p, flags);
-            c->trusted_orders = was;
-            if (rc) return rc;
-            if (overlap) PZ_CUDA(cudaEventRecord(c->super_free[b], c->stream));
-            else if (k + 1 < sizes.size()) { rc = generate(k + 1, offs[k + 1]); if (rc) return rc; }
-        }
-        PZ_CUDA(cudaStreamSynchronize(sg));
-        if (c->profiling) collect_phases(c);
-        return PZ_OK;
-    }
     if (flags & PZ_FUSE_MICRO) { rc = ensure_acc(c); if (rc) return rc; }
     // everything issued so far on the main stream (graph, weights, resets) must
     // be visible to the side streams
@@ -764,7 +664,7 @@ int pz_run_fused(pz_ctx *c, int32_t R, int perm_mode, const void *perm_src, int 
     const int P = c->num_p;
     const int pipeline = (base_mode == PZ_PERM_HOST || base_mode == PZ_PERM_DEVICE) ? 0
                          : c->pipeline >= 0 ? c->pipeline
-                         : (base_mode == PZ_PERM_FEISTEL ? 2 : 0);
+                         : (base_mode == PZ_PERM_PHILOX ? 0 : 2);     // (the bucketed shuffle needs shared memory)
     // three slots rotate even on one stream: the host then runs up to two chunks ahead of the
     // device instead of waiting for every chunk's statistics before it launches the next sweep
     const int nslot = pz_ctx::PZ_SLOTS;

@@ -347,142 +347,123 @@ cudaError_t launch_perm_feistel(int32_t M, int32_t R, const uint32_t *seeds, int
 }
 
 // ---------------------------------------------------------------------------
-// NumPy legacy stream: MT19937 + masked-rejection Fisher-Yates
-// ---------------------------------------------------------------------------
-__global__ void iota_rows_kernel(int32_t M, int32_t R, int32_t *perms)
-{
-    const size_t total = (size_t)M * R;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (size_t)gridDim.x * blockDim.x)
-        perms[i] = (int32_t)(i % (size_t)M);
-}
-
-// One thread per run.  The shuffle is a serial chain, but only through memory: the
-// target j of step i comes from the generator alone, so the targets of the next SWQ steps
-// are drawn ahead of time and their x[j] loads are in flight while the current step
-// swaps.  A step that writes a position a queued load has already read (its own target j,
-// which now holds the old x[i]) forwards the new value to that queue entry, so the result
-// is exactly the sequential one.
+// Warp-cooperative Fisher-Yates: ONE WARP PER RUN, 32 shuffle steps at a time.
 //
-// The queue is a shift register of SWQ (target, prefetched value) pairs, head at index 0,
-// empty entries marked by target -1.  push() executes the head's step (if any), shifts,
-// and appends the new target at the tail; SWQ pushes of the empty marker drain it.
-#ifndef PZ_MTQ
-#define PZ_MTQ 8
+// The shuffle  for i = M-1 .. 1: j = draw(i); swap(x[i], x[j])  is a serial chain only through
+// memory: the targets j come from the generator alone.  A warp therefore draws the targets of a
+// ROW of up to 32 consecutive steps at once (lane l = the l-th step of the row, in stream order)
+// and applies them together: the steps of a row commute unless two of them touch the same
+// position, i.e. two steps share a target (found with match.any) or a step's target is the own
+// position i of a later step of the row (a range test).  Both are rare while i is large (about
+// 32^2 / i per row); a row with a collision is cut at the first step that collides with an
+// earlier one of the same segment and applied segment by segment, in order -- so the result is
+// exactly the sequential one for every M, also for the last few hundred steps, where nearly
+// every row is cut.  Rows are applied one behind the draws: the targets of row g+1 are known
+// (and their lines prefetched into L2) while row g waits for its loads, so a row costs about one
+// L2 round trip for 32 steps instead of one dependent memory access per step and thread.
+//
+// Generators (template parameter):
+//  * MT19937, NumPy's legacy stream bit for bit.  The 624-word state lives in REGISTERS, word
+//    32 r + l in register r of lane l (20 registers; row 19 is half full).  A row of the next
+//    generation needs words k, k+1 and k+397 (mod 624) only, i.e. the same row shifted by one
+//    lane and one other row rotated by 13 (or 29) lanes: four shuffles for 32 words.  The
+//    masked-rejection draw (numpy's legacy interval: smallest 2^k - 1 >= i, redraw above i)
+//    couples a step to the number of draws accepted before it; inside a row that is a ballot
+//    and a population count as long as no draw falls into the 31 values below the row's first i
+//    (else, and whenever the mask changes inside the row, the row is decided lane by lane).
+//  * Philox4x32-10 counter-based draws (PZ_PERM_PHILOX_FY): step i takes word i & 3 of counter
+//    (i >> 2, 0, 0, 4) under key (seed, 'PERC'), unbiased by Lemire's method (rare rejections
+//    take words of (i, attempt, 0, 5)); restated on the CPU in oracle/pz_oracle.c.
+//
+// No shared memory, 8 warps per CTA and at most 64 registers: one such CTA fits next to the
+// sweep CTA that owns the rest of the SM, so the bond orders of the next batch of runs are
+// generated underneath the sweep of the current one.
+// ---------------------------------------------------------------------------
+static constexpr int WP_WARPS = 8;
+#ifndef PZ_WP_DEPTH
+#define PZ_WP_DEPTH 2              // rows drawn (and prefetched) ahead of the row being applied
 #endif
-static constexpr int SWQ = PZ_MTQ;
+static constexpr uint32_t FULL = 0xffffffffu;
 
-struct SwapQueue {
-    int32_t jq[SWQ], vq[SWQ];
-    int32_t *x;
-    int32_t i;                           // step the head entry belongs to
-    __device__ __forceinline__ void init(int32_t *x_, int32_t M) {
-        x = x_; i = M - 1;
-#pragma unroll
-        for (int k = 0; k < SWQ; ++k) { jq[k] = -1; vq[k] = 0; }
-    }
-    // j < 0: the empty marker (drains the queue)
-    __device__ __forceinline__ void push(int32_t jn) {
-        const int32_t j = jq[0];
-        int32_t a = 0;
-        if (j >= 0) {                    // step i: swap x[i] and x[j]
-            a = x[i];
-            const int32_t b = (j == i) ? a : vq[0];
-            x[i] = b;
-            x[j] = a;
-            --i;
-            // x[i] runs down the row one element per step: fetch its line ahead of the dependent load
-            if ((i & 7) == 7 && i >= 64)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(x + (i - 64)));
-        }
-        // shift, forwarding this step's write of x[j] to loads that came too early
-        // (a queued target is below i, so it never equals position i)
-#pragma unroll
-        for (int k = 0; k + 1 < SWQ; ++k) {
-            const int32_t jj = jq[k + 1];
-            int32_t vv = vq[k + 1];
-            if (jj == j) vv = a;
-            jq[k] = jj; vq[k] = vv;
-        }
-        jq[SWQ - 1] = jn;
-        vq[SWQ - 1] = jn >= 0 ? x[jn] : 0;     // behind this step's stores in program order
-    }
-    __device__ __forceinline__ void drain() {
-#pragma unroll 1
-        for (int k = 0; k < SWQ; ++k) push(-1);
-    }
+struct WarpRow {
+    uint32_t acc;                  // lanes that hold a step (warp-uniform)
+    int32_t first;                 // i of the row's first step (warp-uniform)
+    int32_t i, j;                  // this lane's step
 };
 
-// NumPy's stream.  The twister state of a run is one CONTIGUOUS 2.5 KB row of global memory
-// (thread-local arrays are interleaved word by word across the lanes of a warp, and lanes that
-// have rejected different numbers of draws then touch 32 different lines per access).  The state
-// is advanced in place EIGHT words at a time -- element k of the next generation needs only
-// elements k, k+1 and k+397 (mod 624), so a block of eight is independent of itself -- instead
-// of all 624 at once: with the block regeneration of the textbook code every lane of a warp
-// reaches its regeneration at a different step (the lanes have rejected different numbers of
-// draws), each of those runs with one active lane, and the warp pays 32 serial regenerations
-// per 468 steps: that, not the shuffle, was 95 % of the kernel (8.6e9 bonds/s).
-// Every lane then looks at the same draw q of its block in lock step; a draw is either
-// accepted (masked value <= i: one shuffle step) or rejected (nothing happens), so there is
-// no rejection LOOP for lanes to diverge in.
-__global__ void __launch_bounds__(64) perm_mt19937_kernel(int32_t M, int32_t R, const uint32_t *seeds,
-                                                           int32_t *perms, uint32_t *states)
+__device__ __forceinline__ void wp_swap(int32_t *x, int32_t i, int32_t j)
 {
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
-    for (int run = tid; run < R; run += nthr) {
-        uint32_t *mt = states + (size_t)tid * 624;
-        {
-            uint32_t v = seeds[run];
-            mt[0] = v;
-            for (int i = 1; i < 624; ++i) { v = 1812433253u * (v ^ (v >> 30)) + (uint32_t)i; mt[i] = v; }
-        }
-        int k0 = 0;                          // next block of the state row (multiple of 8)
-        SwapQueue q;
-        q.init(perms + (size_t)run * M, M);
-        int32_t i_fill = M - 1;              // next step to draw a target for
-        while (i_fill >= 1) {
-            uint32_t a[9], d[8];
-            {
-                const uint4 lo = *reinterpret_cast<const uint4 *>(mt + k0);
-                const uint4 hi = *reinterpret_cast<const uint4 *>(mt + k0 + 4);
-                a[0] = lo.x; a[1] = lo.y; a[2] = lo.z; a[3] = lo.w;
-                a[4] = hi.x; a[5] = hi.y; a[6] = hi.z; a[7] = hi.w;
-                a[8] = mt[k0 + 8 == 624 ? 0 : k0 + 8];
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                int km = k0 + e + 397;
-                if (km >= 624) km -= 624;
-                const uint32_t y = (a[e] & 0x80000000u) | (a[e + 1] & 0x7fffffffu);
-                d[e] = mt[km] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-            }
-            *reinterpret_cast<uint4 *>(mt + k0) = make_uint4(d[0], d[1], d[2], d[3]);
-            *reinterpret_cast<uint4 *>(mt + k0 + 4) = make_uint4(d[4], d[5], d[6], d[7]);
-            k0 = k0 + 8 == 624 ? 0 : k0 + 8;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                uint32_t y = d[e];
-                y ^= (y >> 11);
-                y ^= (y << 7) & 0x9d2c5680u;
-                y ^= (y << 15) & 0xefc60000u;
-                y ^= (y >> 18);
-                if (i_fill >= 1) {
-                    // numpy legacy rk_interval: smallest 2^k - 1 >= i, masked rejection
-                    const uint32_t j = y & (0xffffffffu >> __clz(i_fill));
-                    if (j <= (uint32_t)i_fill) { q.push((int32_t)j); --i_fill; }
-                }
-            }
-        }
-        q.drain();
+    const int32_t a = x[i], b = x[j];
+    x[i] = b;
+    x[j] = a;
+}
+
+// apply the steps of one row in order (see above); ends with the warp's stores ordered in front of
+// everything that follows
+__device__ __forceinline__ void wp_apply(int32_t *x, const WarpRow &r, int lane)
+{
+    if (!r.acc) return;
+    const bool act = (r.acc >> lane) & 1u;
+    const int32_t last = r.first - __popc(r.acc) + 1;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t peers = __match_any_sync(FULL, act ? (uint32_t)r.j : (0x80000000u | (uint32_t)lane)) & r.acc;
+    const bool dup = act && (peers & lt);                    // an earlier step has the same target
+    const bool hit = act && r.j >= last && r.j < r.i;        // my target is a later step's own position
+    if (!__ballot_sync(FULL, dup || hit)) {
+        if (act) wp_swap(x, r.i, r.j);
+        __syncwarp();
+        return;
+    }
+    uint32_t victim = 32u;                                   // the lane whose step sits on my target
+    if (hit) victim = __fns(r.acc, 0, (r.first - r.j) + 1);
+    int start = 0;
+    while (start < 32) {
+        const uint32_t seg = r.acc & ~((1u << start) - 1u);  // steps still to do
+        if (!seg) break;
+        const uint32_t c1 = __ballot_sync(FULL, act && lane >= start && (peers & lt & seg));
+        int cut = c1 ? __ffs(c1) - 1 : 32;
+        const uint32_t v = __reduce_min_sync(FULL, (hit && lane >= start) ? victim : 32u);
+        if ((int)v < cut) cut = (int)v;
+        if (act && lane >= start && lane < cut) wp_swap(x, r.i, r.j);
+        __syncwarp();
+        start = cut;
     }
 }
 
-// Textbook Fisher-Yates with counter-based draws (PZ_PERM_PHILOX_FY): for i = M-1 .. 1,
-// j = unbiased (Lemire) draw in [0, i] from word i & 3 of Philox4x32-10 counter (i >> 2, 0, 0, 4)
-// under key (seed, 'PERC'); on the (rare, < 2^-15) Lemire rejection words 0.. of counters
-// (i, attempt >= 1, 0, 5).  One thread per run, no shared memory and no state: like the
-// MT19937 kernel it runs underneath the sweep of the previous batch of runs.
-// oracle/pz_oracle.c restates it on the CPU (philox_fy_permutation).
+// numpy's masked rejection for one row of 32-bit draws y (lane order = stream order)
+__device__ __forceinline__ void wp_accept_mt(uint32_t y, int nvalid, int32_t &i, WarpRow &r, int lane)
+{
+    r.first = i;
+    const uint32_t mask = 0xffffffffu >> __clz(i);
+    const uint32_t m = y & mask;
+    const bool le = lane < nvalid && m <= (uint32_t)i;
+    const bool stable = i - 31 > (int32_t)(mask >> 1);       // one mask for the whole row, i stays >= 1
+    const bool amb = le && (int32_t)m > i - 31;
+    if (stable && !__any_sync(FULL, amb)) {
+        r.acc = __ballot_sync(FULL, le);
+        r.i = i - __popc(r.acc & ((1u << lane) - 1u));
+        r.j = (int32_t)m;
+        i -= __popc(r.acc);
+        return;
+    }
+    uint32_t acc = 0;
+    int32_t cur = i;
+    r.i = 0; r.j = 0;
+    for (int l = 0; l < nvalid; ++l) {
+        const uint32_t yl = __shfl_sync(FULL, y, l);
+        if (cur >= 1) {
+            const uint32_t ml = yl & (0xffffffffu >> __clz(cur));
+            if (ml <= (uint32_t)cur) {
+                if (lane == l) { r.i = cur; r.j = (int32_t)ml; }
+                acc |= 1u << l;
+                --cur;
+            }
+        }
+    }
+    r.acc = acc;
+    i = cur;
+}
+
 __device__ __forceinline__ uint32_t philox_fy_bounded(uint32_t seed, uint32_t i, uint32_t w)
 {
     const uint32_t range = i + 1u;
@@ -501,31 +482,135 @@ __device__ __forceinline__ uint32_t philox_fy_bounded(uint32_t seed, uint32_t i,
     }
 }
 
-__global__ void __launch_bounds__(64) perm_philox_fy_kernel(int32_t M, int32_t R, const uint32_t *seeds,
-                                                             int32_t *perms)
-{
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
-    for (int run = tid; run < R; run += nthr) {
-        const uint32_t seed = seeds[run];
-        SwapQueue q;
-        q.init(perms + (size_t)run * M, M);
-        for (int32_t g = (M - 1) >> 2; g >= 0; --g) {
-            uint32_t o[4];
-            philox4x32_10(seed, PHILOX_KEY1, (uint32_t)g, 0u, 0u, 4u, o);
+struct WarpRowQueue {
+    WarpRow q[PZ_WP_DEPTH];
+    __device__ __forceinline__ void init() {
 #pragma unroll
-            for (int e = 3; e >= 0; --e) {
-                const int32_t i = 4 * g + e;
-                if (i >= 1 && i <= M - 1) q.push((int32_t)philox_fy_bounded(seed, (uint32_t)i, o[e]));
-            }
-        }
-        q.drain();
+        for (int k = 0; k < PZ_WP_DEPTH; ++k) q[k].acc = 0u;
     }
+    // apply the oldest row, queue the new one (its targets are prefetched here)
+    __device__ __forceinline__ void push(int32_t *x, const WarpRow &r, int lane) {
+        if (r.acc) {
+            if ((r.acc >> lane) & 1u) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + r.j));
+            // x[i] runs down the row: keep its lines ahead of the loads
+            if (lane == 0 && r.first >= 256) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + (r.first - 256)));
+        }
+        wp_apply(x, q[0], lane);
+#pragma unroll
+        for (int k = 0; k + 1 < PZ_WP_DEPTH; ++k) q[k] = q[k + 1];
+        q[PZ_WP_DEPTH - 1] = r;
+    }
+    __device__ __forceinline__ void drain(int32_t *x, int lane) {
+#pragma unroll
+        for (int k = 0; k < PZ_WP_DEPTH; ++k) wp_apply(x, q[k], lane);
+    }
+};
+
+__device__ __forceinline__ void wp_iota(int32_t *x, int32_t M, int lane)
+{
+    if ((((uintptr_t)x) & 15u) == 0) {
+        int4 *x4 = reinterpret_cast<int4 *>(x);
+        const int n4 = M >> 2;
+        for (int k = lane; k < n4; k += 32) x4[k] = make_int4(4 * k, 4 * k + 1, 4 * k + 2, 4 * k + 3);
+        for (int k = (n4 << 2) + lane; k < M; k += 32) x[k] = k;
+    } else {
+        for (int k = lane; k < M; k += 32) x[k] = k;
+    }
+    __syncwarp();
 }
 
-// runs of one launch of the thread-per-run kernels: at most SERIAL_CTAS_PER_SM CTAs of 64 threads
-// per SM, so that a sweep CTA (46 K registers, all of the shared memory) still fits next to them
-static constexpr int SERIAL_CTAS_PER_SM = 4;
-int perm_serial_capacity(int sms) { return sms * SERIAL_CTAS_PER_SM * 64; }
+// row r of the next twister generation (see the layout above); `s` is indexed statically
+#define PZ_MT_ROW(r)                                                                                   \
+    {                                                                                                  \
+        const uint32_t cur = s[r];                                                                     \
+        const uint32_t t1 = __shfl_down_sync(FULL, cur, 1);                                            \
+        const uint32_t t2 = __shfl_sync(FULL, s[((r) + 1) % 20], 0);                                   \
+        const uint32_t nxt = (lane == ((r) == 19 ? 15 : 31)) ? t2 : t1;                                \
+        uint32_t far;                                                                                  \
+        if ((r) <= 6) {                                                                                \
+            const uint32_t fa = __shfl_sync(FULL, s[((r) + 12) % 20], (lane + 13) & 31);               \
+            const uint32_t fb = __shfl_sync(FULL, s[((r) + 13) % 20], (lane + 13) & 31);               \
+            far = lane < 19 ? fa : fb;                                                                 \
+        } else if ((r) == 7) {                                                                         \
+            const uint32_t fa = __shfl_sync(FULL, s[19], (lane + 13) & 31);                            \
+            const uint32_t fb = __shfl_sync(FULL, s[0], (lane + 29) & 31);                             \
+            far = lane < 3 ? fa : fb;                                                                  \
+        } else {                                                                                       \
+            const uint32_t fa = __shfl_sync(FULL, s[((r) + 12) % 20], (lane + 29) & 31);               \
+            const uint32_t fb = __shfl_sync(FULL, s[((r) + 13) % 20], (lane + 29) & 31);               \
+            far = lane < 3 ? fa : fb;      /* rows r - 8 and r - 7 (mod 20), already of this generation */ \
+        }                                                                                              \
+        const uint32_t yy = (cur & 0x80000000u) | (nxt & 0x7fffffffu);                                 \
+        uint32_t v = far ^ (yy >> 1) ^ ((yy & 1u) ? 0x9908b0dfu : 0u);                                 \
+        s[r] = v;                                                                                      \
+        v ^= (v >> 11);                                                                                \
+        v ^= (v << 7) & 0x9d2c5680u;                                                                   \
+        v ^= (v << 15) & 0xefc60000u;                                                                  \
+        v ^= (v >> 18);                                                                                \
+        y[r] = v;                                                                                      \
+    }
+
+template <bool MT>
+__global__ void __launch_bounds__(32 * WP_WARPS, 4) perm_warp_kernel(int32_t M, int32_t R, const uint32_t *seeds,
+                                                                      int32_t *perms)
+{
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * WP_WARPS + (threadIdx.x >> 5), nw = gridDim.x * WP_WARPS;
+    for (int run = gw; run < R; run += nw) {
+        int32_t *x = perms + (size_t)run * M;
+        const uint32_t seed = seeds[run];
+        wp_iota(x, M, lane);
+        WarpRowQueue Q;
+        Q.init();
+        int32_t i = M - 1;                   // next step to draw a target for
+        if (MT) {
+            uint32_t s[20], y[20];
+            {
+                // init_genrand: a serial recurrence, computed by every lane; lane l keeps word 32 r + l
+                uint32_t v = seed;
+#pragma unroll
+                for (int r = 0; r < 20; ++r) {
+                    s[r] = 0u;
+#pragma unroll 1
+                    for (int l = 0; l < 32; ++l) {
+                        if (lane == l) s[r] = v;
+                        v = 1812433253u * (v ^ (v >> 30)) + (uint32_t)(32 * r + l + 1);
+                    }
+                }
+            }
+            while (i >= 1) {
+                PZ_MT_ROW(0) PZ_MT_ROW(1) PZ_MT_ROW(2) PZ_MT_ROW(3) PZ_MT_ROW(4)
+                PZ_MT_ROW(5) PZ_MT_ROW(6) PZ_MT_ROW(7) PZ_MT_ROW(8) PZ_MT_ROW(9)
+                PZ_MT_ROW(10) PZ_MT_ROW(11) PZ_MT_ROW(12) PZ_MT_ROW(13) PZ_MT_ROW(14)
+                PZ_MT_ROW(15) PZ_MT_ROW(16) PZ_MT_ROW(17) PZ_MT_ROW(18) PZ_MT_ROW(19)
+#pragma unroll 1
+                for (int r = 0; r < 20 && i >= 1; ++r) {
+                    WarpRow row;
+                    wp_accept_mt(y[r], r == 19 ? 16 : 32, i, row, lane);
+                    Q.push(x, row, lane);
+                }
+            }
+        } else {
+            while (i >= 1) {
+                WarpRow row;
+                row.first = i;
+                row.i = i - lane;
+                const bool act = row.i >= 1;
+                row.acc = __ballot_sync(FULL, act);
+                row.j = 0;
+                if (act) {
+                    uint32_t o[4];
+                    philox4x32_10(seed, PHILOX_KEY1, (uint32_t)row.i >> 2, 0u, 0u, 4u, o);
+                    const uint32_t w = (row.i & 2) ? ((row.i & 1) ? o[3] : o[2]) : ((row.i & 1) ? o[1] : o[0]);
+                    row.j = (int32_t)philox_fy_bounded(seed, (uint32_t)row.i, w);
+                }
+                i -= __popc(row.acc);
+                Q.push(x, row, lane);
+            }
+        }
+        Q.drain(x, lane);
+    }
+}
 
 static cudaError_t launch_perm_serial(int mode_mt, int32_t M, int32_t R, const uint32_t *seeds,
                                       int32_t *perms, cudaStream_t s, int *launches)
@@ -535,27 +620,15 @@ static cudaError_t launch_perm_serial(int mode_mt, int32_t M, int32_t R, const u
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int ctas = (R + 63) / 64;
-    // more runs than one co-resident launch holds: threads take several runs in turn
-    // (PZ_SERIAL_FULL=1: as many threads as runs -- when nothing has to fit next to the kernel)
-    static const bool full = getenv("PZ_SERIAL_FULL") && atoi(getenv("PZ_SERIAL_FULL"));
-    if (!full && ctas > sms * SERIAL_CTAS_PER_SM) ctas = sms * SERIAL_CTAS_PER_SM;
-    uint32_t *states = nullptr;
-    cudaError_t e = cudaSuccess;
-    if (mode_mt) {
-        e = cudaMallocAsync(&states, (size_t)ctas * 64 * 624 * sizeof(uint32_t), s);
-        if (e != cudaSuccess) return e;
-    }
-    iota_rows_kernel<<<1184, 256, 0, s>>>(M, R, perms);
-    if (mode_mt) perm_mt19937_kernel<<<ctas, 64, 0, s>>>(M, R, seeds, perms, states);
-    else perm_philox_fy_kernel<<<ctas, 64, 0, s>>>(M, R, seeds, perms);
-    *launches = 2;
-    e = cudaGetLastError();
-    if (mode_mt) {
-        const cudaError_t e2 = cudaFreeAsync(states, s);
-        if (e == cudaSuccess) e = e2;
-    }
-    return e;
+    // up to four CTAs per SM when the kernel has the SMs to itself; next to a sweep only one of
+    // them is resident at a time and the others follow as the sweep's CTAs retire
+    static const int per_sm = getenv("PZ_WP_CTAS") ? std::max(1, atoi(getenv("PZ_WP_CTAS"))) : 4;
+    int ctas = (R + WP_WARPS - 1) / WP_WARPS;
+    if (ctas > sms * per_sm) ctas = sms * per_sm;
+    if (mode_mt) perm_warp_kernel<true><<<ctas, 32 * WP_WARPS, 0, s>>>(M, R, seeds, perms);
+    else perm_warp_kernel<false><<<ctas, 32 * WP_WARPS, 0, s>>>(M, R, seeds, perms);
+    *launches = 1;
+    return cudaGetLastError();
 }
 
 cudaError_t launch_perm_mt19937(int32_t M, int32_t R, const uint32_t *seeds, int32_t *perms,

@@ -1,5 +1,5 @@
 """GPU parity tests added in round 2: the thread-per-run bond-order generators and their
-double-buffered super-chunks, validation of caller-supplied bond orders, claim-epoch rebasing,
+bond orders generated under the sweep, validation of caller-supplied bond orders, claim-epoch rebasing,
 the 64-bit-record canonical kernels, more full-size runs, statistical validation of every
 generator at L = 256, and the measured floating-point error of every averaged column against
 an exact rational evaluation."""
@@ -57,9 +57,9 @@ def test_philox_fy_bond_orders_match_restatement():
 
 
 @pytest.mark.parametrize("mode_name", ["PERM_MT19937", "PERM_PHILOX_FY"])
-def test_thread_per_run_generators_with_more_runs_than_threads(mode_name):
-    """A launch of the thread-per-run kernels holds at most SMs x 4 x 64 threads (so that a sweep
-    CTA still fits next to it); with more runs every thread takes several in turn."""
+def test_warp_per_run_generators_with_more_runs_than_warps(mode_name):
+    """A launch of the warp-per-run kernels holds at most SMs x 4 CTAs of 8 warps; with more runs
+    every warp takes several in turn."""
     from pypercolate_b200 import lowering
     from oracle import oracle
     n = _native()
@@ -79,9 +79,9 @@ def test_thread_per_run_generators_with_more_runs_than_threads(mode_name):
 
 @pytest.mark.parametrize("pipeline", [None, 0])
 @pytest.mark.parametrize("mode_name", ["PERM_MT19937", "PERM_PHILOX_FY"])
-def test_double_buffered_super_chunks_are_exact(mode_name, pipeline):
-    """The fused path generates the bond orders of super-chunk k+1 on a second stream underneath
-    the sweeps of super-chunk k (two buffers).  Seven super-chunks of 100 runs must give exactly
+def test_bond_orders_generated_under_the_sweep_are_exact(mode_name, pipeline):
+    """The fused path generates the bond orders of chunk k+1 on a second stream underneath the
+    sweep of chunk k (three rotating slots).  Seven chunks of about 100 runs must give exactly
     the sums of one batch swept from host-supplied orders."""
     from pypercolate_b200 import lowering
     from oracle import oracle
@@ -98,7 +98,7 @@ def test_double_buffered_super_chunks_are_exact(mode_name, pipeline):
     base.run_fused(runs, n.PERM_HOST, perms, n.FUSE_MICRO | n.FUSE_CANON)
     want_acc, want_canon = base.micro_export(), base.canon_export()
     base.close()
-    over = dict(PZ_SUPER_RUNS=100)
+    over = dict(PZ_CHUNK_BYTES=9000000)
     if pipeline is not None:
         over["PZ_PIPELINE"] = pipeline
     with env(**over):
@@ -453,7 +453,20 @@ def test_measured_float_error_of_reduced_and_finalized_columns(name, capsys):
         e_gpu, e_ref, e_gr = _rel(got, exact), _rel(ref, exact), _rel(got, ref)
         fin = np.isfinite(e_gpu) & np.isfinite(e_ref)
         report.append((kind, e_gr[fin].max(), e_gpu[fin].max(), e_ref[fin].max()))
-        assert np.all(e_gpu[fin] <= np.maximum(1e-10, 4 * e_ref[fin])), kind
+        allowed = np.maximum(1e-10, 4 * e_ref)
+        if kind == 'm2':
+            # conditioning: an M2 far below runs * mean^2 is not determined to 1e-10 by per-run values
+            # that are themselves rounded doubles -- perturbing every input by d = 4 ulp moves
+            # M2 by up to 2 sqrt(M2 runs) d |mean| + runs (d mean)^2 (hpc_grid8: the spanning
+            # probability at a p where every run is 1 - 1e-8: M2 = 9.7e-15, and the REFERENCE's own
+            # value is 4.2e-10 off the exact one)
+            dlt = 4 * np.finfo(np.float64).eps * np.abs(exact_mean)
+            with np.errstate(divide='ignore', invalid='ignore'):
+                cond = (2 * np.sqrt(np.abs(exact) * runs) * dlt + runs * dlt ** 2) / np.abs(exact)
+            allowed = np.maximum(allowed, np.where(np.isfinite(cond), cond, 0.0))
+        bad = fin & ~(e_gpu <= allowed)
+        assert not bad.any(), (kind, [(int(i), int(c), got[i, c], ref[i, c], exact[i, c])
+                                      for i, c in zip(*np.nonzero(bad))][:5])
         if kind == 'mean':
             assert e_gr[fin].max() <= 1e-10
     # finalized columns: exact std from the exact M2; ci = mean + t * std / sqrt(n) (scipy quantile)
@@ -484,7 +497,12 @@ def test_measured_float_error_of_reduced_and_finalized_columns(name, capsys):
         e_gpu, e_ref, e_gr = _rel(got, exact), _rel(ref, exact), _rel(got, ref)
         ok = np.isfinite(e_gpu) & np.isfinite(e_ref) & (exact_std > 0)
         report.append((label, e_gr[ok].max(), e_gpu[ok].max(), e_ref[ok].max()))
-        assert np.all(e_gpu[ok] <= np.maximum(1e-10, 4 * e_ref[ok])), label
+        allowed = np.maximum(1e-10, 4 * e_ref)
+        if label == 'std':           # sqrt halves the relative error of the ill-conditioned M2 (see above)
+            allowed = np.maximum(allowed, np.where(np.isfinite(cond), cond, 0.0))
+        bad = ok & ~(e_gpu <= allowed)
+        assert not bad.any(), (label, [(int(i), int(c), got[i, c], ref[i, c], exact[i, c])
+                                       for i, c in zip(*np.nonzero(bad))][:5])
     with capsys.disabled():
         print("\n[%s] max relative error   GPU vs reference | GPU vs exact | reference vs exact" % name)
         for label, a, b, c in report:
