@@ -373,7 +373,7 @@ cudaError_t launch_perm_feistel(int32_t M, int32_t R, const uint32_t *seeds, int
 //    (else, and whenever the mask changes inside the row, the row is decided lane by lane).
 //  * Philox4x32-10 counter-based draws (PZ_PERM_PHILOX_FY): step i takes word i & 3 of counter
 //    (i >> 2, 0, 0, 4) under key (seed, 'PERC'), unbiased by Lemire's method (rare rejections
-//    take words of (i, attempt, 0, 5)); restated on the CPU in oracle/pz_oracle.c.
+//    take words of (i, attempt, 0, 5)); the tests hold a CPU restatement.
 //
 // No shared memory, 8 warps per CTA and at most 64 registers: one such CTA fits next to the
 // sweep CTA that owns the rest of the SM, so the bond orders of the next batch of runs are
