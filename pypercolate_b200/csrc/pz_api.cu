@@ -111,6 +111,7 @@ struct pz_ctx {
     DevBuf<double> pmf;                   // [num_p][M+1], rows in ascending-p order
     DevBuf<int32_t> band_lo, band_hi, tband_lo, tband_hi, porder_dev, canon_flags;
     DevBuf<double> sf;                    // survival functions [num_p][M+1]
+    DevBuf<int32_t> perm_stage;           // warp-per-run shuffles: one L2-resident staging row per warp
     DevBuf<uint32_t> validate_bits;       // caller-supplied orders: one bit per (run, bond) + flag word
     int *validate_host = nullptr;         // pinned copy of the flag word
     uint32_t epoch_start = 0x003fffffu;   // first claim epoch of a run (PZ_EPOCH_START: tests)
@@ -199,24 +200,30 @@ cudaError_t launch_canon_reduce(int32_t R, int32_t cols, const double *runs, dou
 cudaError_t launch_perm_philox(int32_t M, int32_t R, const uint32_t *seeds, int32_t *perms,
                                cudaStream_t s, int *launches);
 cudaError_t launch_perm_mt19937(int32_t M, int32_t R, const uint32_t *seeds, int32_t *perms,
-                                cudaStream_t s, int *launches);
+                                int32_t *stage, cudaStream_t s, int *launches);
+size_t perm_stage_ints(int sms, int32_t M);
 cudaError_t launch_perm_feistel(int32_t M, int32_t R, const uint32_t *seeds, int32_t *perms,
                                 cudaStream_t s, int *launches);
 cudaError_t launch_perm_philox_fy(int32_t M, int32_t R, const uint32_t *seeds, int32_t *perms,
-                                  cudaStream_t s, int *launches);
+                                  int32_t *stage, cudaStream_t s, int *launches);
 cudaError_t launch_validate_orders(int32_t M, int32_t R, const int32_t *perms, uint32_t *bitmap,
                                    int *flag, cudaStream_t s);
 }
 
-static cudaError_t launch_perm_mode(int perm_mode, int32_t M, int32_t R, const uint32_t *seeds,
+static cudaError_t launch_perm_mode(pz_ctx *c, int perm_mode, int32_t M, int32_t R, const uint32_t *seeds,
                                     int32_t *perms, cudaStream_t s, int *l)
 {
     switch (perm_mode) {
     case PZ_PERM_PHILOX: return launch_perm_philox(M, R, seeds, perms, s, l);
     case PZ_PERM_FEISTEL: return launch_perm_feistel(M, R, seeds, perms, s, l);
-    case PZ_PERM_PHILOX_FY: return launch_perm_philox_fy(M, R, seeds, perms, s, l);
-    default: return launch_perm_mt19937(M, R, seeds, perms, s, l);
+    default: break;
     }
+    // warp-per-run shuffles: one staging row per warp of the launch (allocated once per graph size;
+    // launches of one context are ordered on a stream, so they never share it concurrently)
+    cudaError_t e = c->perm_stage.ensure(perm_stage_ints(c->sms, M));
+    if (e != cudaSuccess) return e;
+    if (perm_mode == PZ_PERM_PHILOX_FY) return launch_perm_philox_fy(M, R, seeds, perms, c->perm_stage.p, s, l);
+    return launch_perm_mt19937(M, R, seeds, perms, c->perm_stage.p, s, l);
 }
 
 extern "C" {
@@ -282,6 +289,7 @@ void pz_destroy(pz_ctx *c)
         if (sl.stats_done) cudaEventDestroy(sl.stats_done);
     }
     c->validate_bits.release();
+    c->perm_stage.release();
     if (c->validate_host) cudaFreeHost(c->validate_host);
     pz_comm_destroy(c);
     c->comm_send.release(); c->comm_recv.release();
@@ -444,7 +452,7 @@ static int sweep_chunk(pz_ctx *c, pz_ctx::Slot &sl, cudaStream_t sp, int32_t R, 
             }
             int l = 0;
             PhaseTimer t(c, PZ_PHASE_PERM, sp);
-            PZ_CUDA(launch_perm_mode(perm_mode, M, R, seeds_dev, sl.perms.p, sp, &l));
+            PZ_CUDA(launch_perm_mode(c, perm_mode, M, R, seeds_dev, sl.perms.p, sp, &l));
             c->launches += l;
         }
     }
@@ -610,7 +618,7 @@ int pz_make_perms(pz_ctx *c, int32_t R, int perm_mode, const uint32_t *seeds, in
         int l = 0;
         {
             PhaseTimer t(c, PZ_PHASE_PERM);
-            PZ_CUDA(launch_perm_mode(perm_mode, c->M, n, sl.seeds.p, dst, c->stream, &l));
+            PZ_CUDA(launch_perm_mode(c, perm_mode, c->M, n, sl.seeds.p, dst, c->stream, &l));
         }
         c->launches += l;
         if (!is_device)

@@ -379,10 +379,7 @@ cudaError_t launch_perm_feistel(int32_t M, int32_t R, const uint32_t *seeds, int
 // sweep CTA that owns the rest of the SM, so the bond orders of the next batch of runs are
 // generated underneath the sweep of the current one.
 // ---------------------------------------------------------------------------
-static constexpr int WP_WARPS = 8;
-#ifndef PZ_WP_DEPTH
-#define PZ_WP_DEPTH 2              // rows drawn (and prefetched) ahead of the row being applied
-#endif
+static constexpr int WP_WARPS = 8;             // most warps a CTA of the kernel may have
 static constexpr uint32_t FULL = 0xffffffffu;
 
 struct WarpRow {
@@ -390,45 +387,6 @@ struct WarpRow {
     int32_t first;                 // i of the row's first step (warp-uniform)
     int32_t i, j;                  // this lane's step
 };
-
-__device__ __forceinline__ void wp_swap(int32_t *x, int32_t i, int32_t j)
-{
-    const int32_t a = x[i], b = x[j];
-    x[i] = b;
-    x[j] = a;
-}
-
-// apply the steps of one row in order (see above); ends with the warp's stores ordered in front of
-// everything that follows
-__device__ __forceinline__ void wp_apply(int32_t *x, const WarpRow &r, int lane)
-{
-    if (!r.acc) return;
-    const bool act = (r.acc >> lane) & 1u;
-    const int32_t last = r.first - __popc(r.acc) + 1;
-    const uint32_t lt = (1u << lane) - 1u;
-    const uint32_t peers = __match_any_sync(FULL, act ? (uint32_t)r.j : (0x80000000u | (uint32_t)lane)) & r.acc;
-    const bool dup = act && (peers & lt);                    // an earlier step has the same target
-    const bool hit = act && r.j >= last && r.j < r.i;        // my target is a later step's own position
-    if (!__ballot_sync(FULL, dup || hit)) {
-        if (act) wp_swap(x, r.i, r.j);
-        __syncwarp();
-        return;
-    }
-    uint32_t victim = 32u;                                   // the lane whose step sits on my target
-    if (hit) victim = __fns(r.acc, 0, (r.first - r.j) + 1);
-    int start = 0;
-    while (start < 32) {
-        const uint32_t seg = r.acc & ~((1u << start) - 1u);  // steps still to do
-        if (!seg) break;
-        const uint32_t c1 = __ballot_sync(FULL, act && lane >= start && (peers & lt & seg));
-        int cut = c1 ? __ffs(c1) - 1 : 32;
-        const uint32_t v = __reduce_min_sync(FULL, (hit && lane >= start) ? victim : 32u);
-        if ((int)v < cut) cut = (int)v;
-        if (act && lane >= start && lane < cut) wp_swap(x, r.i, r.j);
-        __syncwarp();
-        start = cut;
-    }
-}
 
 // numpy's masked rejection for one row of 32-bit draws y (lane order = stream order)
 __device__ __forceinline__ void wp_accept_mt(uint32_t y, int nvalid, int32_t &i, WarpRow &r, int lane)
@@ -482,40 +440,77 @@ __device__ __forceinline__ uint32_t philox_fy_bounded(uint32_t seed, uint32_t i,
     }
 }
 
-struct WarpRowQueue {
-    WarpRow q[PZ_WP_DEPTH];
-    __device__ __forceinline__ void init() {
-#pragma unroll
-        for (int k = 0; k < PZ_WP_DEPTH; ++k) q[k].acc = 0u;
-    }
-    // apply the oldest row, queue the new one (its targets are prefetched here)
-    __device__ __forceinline__ void push(int32_t *x, const WarpRow &r, int lane) {
-        if (r.acc) {
-            if ((r.acc >> lane) & 1u) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + r.j));
-            // x[i] runs down the row: keep its lines ahead of the loads
-            if (lane == 0 && r.first >= 256) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + (r.first - 256)));
+// The shuffle of one run.  x = the warp's staging row (L2 resident, reused run after run): it holds
+// the live part of the permutation, positions 0..i; position i is final after step i, so its value
+// goes straight to the output row (a coalesced streaming store) and never back to the staging row.
+// Rows are software pipelined: the loads of row g are in flight while row g+1 is drawn and checked
+// for collisions; its stores follow, then the loads of row g+1 (behind the stores in program order
+// and a __syncwarp: a later row may read what an earlier one wrote).
+struct WarpShuffler {
+    int32_t *x, *out;
+    WarpRow p;                     // row whose loads are in flight (p.acc == 0: none)
+    int32_t a, b;
+
+    __device__ __forceinline__ void init(int32_t *x_, int32_t *out_) { x = x_; out = out_; p.acc = 0u; }
+    __device__ __forceinline__ void finish(int lane) {
+        if (!p.acc) return;
+        if ((p.acc >> lane) & 1u) {
+            __stcs(out + p.i, b);
+            x[p.j] = a;
         }
-        wp_apply(x, q[0], lane);
-#pragma unroll
-        for (int k = 0; k + 1 < PZ_WP_DEPTH; ++k) q[k] = q[k + 1];
-        q[PZ_WP_DEPTH - 1] = r;
+        __syncwarp();
+        p.acc = 0u;
     }
-    __device__ __forceinline__ void drain(int32_t *x, int lane) {
-#pragma unroll
-        for (int k = 0; k < PZ_WP_DEPTH; ++k) wp_apply(x, q[k], lane);
+    __device__ __forceinline__ void push(const WarpRow &r, int lane) {
+        if (!r.acc) { return; }
+        const bool act = (r.acc >> lane) & 1u;
+        const int32_t last = r.first - __popc(r.acc) + 1;
+        const uint32_t lt = (1u << lane) - 1u;
+        const uint32_t peers = __match_any_sync(FULL, act ? (uint32_t)r.j : (0x80000000u | (uint32_t)lane)) & r.acc;
+        const bool dup = act && (peers & lt);                    // an earlier step has the same target
+        const bool hit = act && r.j >= last && r.j < r.i;        // my target is a later step's own position
+        const uint32_t confl = __ballot_sync(FULL, dup || hit);
+        finish(lane);                                            // the previous row's stores
+        if (!confl) {
+            if (act) { a = x[r.i]; b = x[r.j]; }
+            p = r;
+            return;
+        }
+        // a row with a collision: cut at the first step that collides with an earlier one of the
+        // same segment, segment by segment, in order
+        uint32_t victim = 32u;                                   // the lane whose step sits on my target
+        if (hit) victim = __fns(r.acc, 0, (r.first - r.j) + 1);
+        int start = 0;
+        while (start < 32) {
+            const uint32_t seg = r.acc & ~((1u << start) - 1u);  // steps still to do
+            if (!seg) break;
+            const uint32_t c1 = __ballot_sync(FULL, act && lane >= start && (peers & lt & seg));
+            int cut = c1 ? __ffs(c1) - 1 : 32;
+            const uint32_t v = __reduce_min_sync(FULL, (hit && lane >= start) ? victim : 32u);
+            if ((int)v < cut) cut = (int)v;
+            if (act && lane >= start && lane < cut) {
+                const int32_t va = x[r.i], vb = x[r.j];
+                __stcs(out + r.i, vb);
+                x[r.j] = va;
+            }
+            __syncwarp();
+            start = cut;
+        }
+    }
+    // after the last step position 0 is final as well
+    __device__ __forceinline__ void done(int32_t M, int lane) {
+        finish(lane);
+        if (lane == 0 && M > 0) __stcs(out, x[0]);
+        __syncwarp();
     }
 };
 
 __device__ __forceinline__ void wp_iota(int32_t *x, int32_t M, int lane)
 {
-    if ((((uintptr_t)x) & 15u) == 0) {
-        int4 *x4 = reinterpret_cast<int4 *>(x);
-        const int n4 = M >> 2;
-        for (int k = lane; k < n4; k += 32) x4[k] = make_int4(4 * k, 4 * k + 1, 4 * k + 2, 4 * k + 3);
-        for (int k = (n4 << 2) + lane; k < M; k += 32) x[k] = k;
-    } else {
-        for (int k = lane; k < M; k += 32) x[k] = k;
-    }
+    int4 *x4 = reinterpret_cast<int4 *>(x);                     // (staging rows are 128-byte aligned)
+    const int n4 = M >> 2;
+    for (int k = lane; k < n4; k += 32) x4[k] = make_int4(4 * k, 4 * k + 1, 4 * k + 2, 4 * k + 3);
+    for (int k = (n4 << 2) + lane; k < M; k += 32) x[k] = k;
     __syncwarp();
 }
 
@@ -552,16 +547,18 @@ __device__ __forceinline__ void wp_iota(int32_t *x, int32_t M, int lane)
 
 template <bool MT>
 __global__ void __launch_bounds__(32 * WP_WARPS, 4) perm_warp_kernel(int32_t M, int32_t R, const uint32_t *seeds,
-                                                                      int32_t *perms)
+                                                                      int32_t *perms, int32_t *stage,
+                                                                      size_t stage_stride)
 {
     const int lane = threadIdx.x & 31;
-    const int gw = blockIdx.x * WP_WARPS + (threadIdx.x >> 5), nw = gridDim.x * WP_WARPS;
+    const int wpc = blockDim.x >> 5;
+    const int gw = blockIdx.x * wpc + (threadIdx.x >> 5), nw = gridDim.x * wpc;
+    int32_t *x = stage + (size_t)gw * stage_stride;
     for (int run = gw; run < R; run += nw) {
-        int32_t *x = perms + (size_t)run * M;
         const uint32_t seed = seeds[run];
         wp_iota(x, M, lane);
-        WarpRowQueue Q;
-        Q.init();
+        WarpShuffler S;
+        S.init(x, perms + (size_t)run * M);
         int32_t i = M - 1;                   // next step to draw a target for
         if (MT) {
             uint32_t s[20], y[20];
@@ -587,60 +584,83 @@ __global__ void __launch_bounds__(32 * WP_WARPS, 4) perm_warp_kernel(int32_t M, 
                 for (int r = 0; r < 20 && i >= 1; ++r) {
                     WarpRow row;
                     wp_accept_mt(y[r], r == 19 ? 16 : 32, i, row, lane);
-                    Q.push(x, row, lane);
+                    S.push(row, lane);
                 }
             }
         } else {
+            // lane L holds the Philox block of counter c0 - L: 128 steps (four rows) per evaluation
+            uint32_t o[4] = {0u, 0u, 0u, 0u};
+            int32_t c0 = -1;
             while (i >= 1) {
                 WarpRow row;
                 row.first = i;
                 row.i = i - lane;
                 const bool act = row.i >= 1;
                 row.acc = __ballot_sync(FULL, act);
-                row.j = 0;
-                if (act) {
-                    uint32_t o[4];
-                    philox4x32_10(seed, PHILOX_KEY1, (uint32_t)row.i >> 2, 0u, 0u, 4u, o);
-                    const uint32_t w = (row.i & 2) ? ((row.i & 1) ? o[3] : o[2]) : ((row.i & 1) ? o[1] : o[0]);
-                    row.j = (int32_t)philox_fy_bounded(seed, (uint32_t)row.i, w);
+                const int32_t c_hi = i >> 2, c_lo = (i - 31 > 0 ? i - 31 : 0) >> 2;
+                if (c0 < 0 || c0 < c_hi || c0 - c_lo > 31) {
+                    c0 = c_hi;
+                    if (c0 - lane >= 0) philox4x32_10(seed, PHILOX_KEY1, (uint32_t)(c0 - lane), 0u, 0u, 4u, o);
                 }
+                const int src = act ? c0 - (row.i >> 2) : 0;
+                const uint32_t w0 = __shfl_sync(FULL, o[0], src), w1 = __shfl_sync(FULL, o[1], src);
+                const uint32_t w2 = __shfl_sync(FULL, o[2], src), w3 = __shfl_sync(FULL, o[3], src);
+                const uint32_t w = (row.i & 2) ? ((row.i & 1) ? w3 : w2) : ((row.i & 1) ? w1 : w0);
+                row.j = act ? (int32_t)philox_fy_bounded(seed, (uint32_t)row.i, w) : 0;
                 i -= __popc(row.acc);
-                Q.push(x, row, lane);
+                S.push(row, lane);
             }
         }
-        Q.drain(x, lane);
+        S.done(M, lane);
     }
 }
 
+// Shape of a launch: one CTA per SM (it has to fit next to a sweep CTA), PZ_WP_WARPS warps each
+// (default 4); every warp owns one staging row.  Few warps keep the staging rows inside the L2.
+void perm_warp_shape(int sms, int32_t M, int *ctas, int *wpc, size_t *stride)
+{
+    static const int per_sm = getenv("PZ_WP_CTAS") ? std::max(1, atoi(getenv("PZ_WP_CTAS"))) : 1;
+    static const int w = getenv("PZ_WP_WARPS") ? std::min(WP_WARPS, std::max(1, atoi(getenv("PZ_WP_WARPS")))) : 4;
+    *ctas = sms * per_sm;
+    *wpc = w;
+    *stride = ((size_t)std::max(M, 1) + 31) / 32 * 32;
+}
+
+size_t perm_stage_ints(int sms, int32_t M)
+{
+    int ctas, wpc; size_t stride;
+    perm_warp_shape(sms, M, &ctas, &wpc, &stride);
+    return (size_t)ctas * wpc * stride;
+}
+
 static cudaError_t launch_perm_serial(int mode_mt, int32_t M, int32_t R, const uint32_t *seeds,
-                                      int32_t *perms, cudaStream_t s, int *launches)
+                                      int32_t *perms, int32_t *stage, cudaStream_t s, int *launches)
 {
     *launches = 0;
     if (R <= 0 || M <= 0) return cudaSuccess;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // up to four CTAs per SM when the kernel has the SMs to itself; next to a sweep only one of
-    // them is resident at a time and the others follow as the sweep's CTAs retire
-    static const int per_sm = getenv("PZ_WP_CTAS") ? std::max(1, atoi(getenv("PZ_WP_CTAS"))) : 4;
-    int ctas = (R + WP_WARPS - 1) / WP_WARPS;
-    if (ctas > sms * per_sm) ctas = sms * per_sm;
-    if (mode_mt) perm_warp_kernel<true><<<ctas, 32 * WP_WARPS, 0, s>>>(M, R, seeds, perms);
-    else perm_warp_kernel<false><<<ctas, 32 * WP_WARPS, 0, s>>>(M, R, seeds, perms);
+    int ctas, wpc; size_t stride;
+    perm_warp_shape(sms, M, &ctas, &wpc, &stride);
+    const int need = (R + wpc - 1) / wpc;
+    if (ctas > need) ctas = need;
+    if (mode_mt) perm_warp_kernel<true><<<ctas, 32 * wpc, 0, s>>>(M, R, seeds, perms, stage, stride);
+    else perm_warp_kernel<false><<<ctas, 32 * wpc, 0, s>>>(M, R, seeds, perms, stage, stride);
     *launches = 1;
     return cudaGetLastError();
 }
 
 cudaError_t launch_perm_mt19937(int32_t M, int32_t R, const uint32_t *seeds, int32_t *perms,
-                                cudaStream_t s, int *launches)
+                                int32_t *stage, cudaStream_t s, int *launches)
 {
-    return launch_perm_serial(1, M, R, seeds, perms, s, launches);
+    return launch_perm_serial(1, M, R, seeds, perms, stage, s, launches);
 }
 
 cudaError_t launch_perm_philox_fy(int32_t M, int32_t R, const uint32_t *seeds, int32_t *perms,
-                                  cudaStream_t s, int *launches)
+                                  int32_t *stage, cudaStream_t s, int *launches)
 {
-    return launch_perm_serial(0, M, R, seeds, perms, s, launches);
+    return launch_perm_serial(0, M, R, seeds, perms, stage, s, launches);
 }
 
 // ---------------------------------------------------------------------------

@@ -1168,6 +1168,365 @@ __global__ void __launch_bounds__(FW_ALL + 256, 1) sweep_fw_kernel(SweepArgs a, 
 }
 
 // ---------------------------------------------------------------------------
+// CTA kernel with finder warps, CARRIED bonds and several HUBS (the shape used for one run per SM).
+//
+// sweep_fw_kernel finishes every batch before it starts the next: once at most 32 bonds are left,
+// warp 0 alone runs warp-level rounds while 15 warps wait (a fifth of all warp samples), and in
+// the critical window (0.44 < n/M < 0.51), where several large clusters compete, star merging
+// around the single largest cluster leaves chains that take one round per bond.  Here
+//
+//  * the (at most 32) bonds still pending when a batch has quietened down are CARRIED into the
+//    next batch as its earliest bonds: a seventeenth main warp, warp 0, holds nothing but carried
+//    bonds (claim keys are the thread index, so they order before every new bond), the other 16
+//    main warps take the 512 new bonds of the batch.  There is no tail mode, no warp waits for
+//    another, and the rounds of the carried bonds are shared with the next batch's;
+//  * star merging works around up to K hubs at once (K = 2 by default): a star bond joins a
+//    non-hub root it owns to hub h, all star bonds of a round below the first blocked bond merge
+//    together, and ONE ordered 64-bit prefix sum (a 21-bit field per hub) gives each the hub
+//    size the sequential order would see.  A bond between two hubs is an ordinary bond that
+//    claims both hub roots; it must not overtake an earlier pending star bond of either hub, and
+//    a star bond must not overtake an earlier hub-hub bond of its hub (it checks the hub's claim
+//    slot without claiming it).  Any set of current roots is a valid hub set; the slots hold the
+//    largest clusters seen (a merged cluster replaces the smallest slot it beats, secondary
+//    hubs from 256 nodes on).
+//
+// Simulated with exact claims (scripts/sim_rounds_hubs_carry.c, records identical to the
+// sequential run): 427 CTA rounds + 213 tails per L = 256 run -> about 465 CTA rounds, no tails.
+// Everything else (finder warps, release/acquire hand-over of the forest, count-first rounds,
+// epoch-keyed claims) is sweep_fw_kernel's.
+// ---------------------------------------------------------------------------
+static constexpr int FC_NEW_WARPS = 16, FC_MAIN_WARPS = FC_NEW_WARPS + 1;
+static constexpr int FC_NEW = 32 * FC_NEW_WARPS, FC_MAIN = 32 * FC_MAIN_WARPS;       // 512, 544
+static constexpr int FC_FIND = FW_FIND, FC_ALL = FC_MAIN + FC_FIND;                   // 128, 672
+static constexpr int FC_PAIR = FC_NEW + FC_FIND;                                      // hand-over barriers
+static constexpr int FC_BPT = FC_NEW / FC_FIND;
+static constexpr int FC_MAX_HUBS = 3;
+#ifndef PZ_HUB_MIN
+#define PZ_HUB_MIN 256                        // smallest cluster that may become a secondary hub
+#endif
+
+struct FcShared {
+    unsigned long long hubk[FC_MAX_HUBS];     // (size << 32) | root of hub k, 0 = empty slot
+    unsigned long long scan_tot[FC_MAIN_WARPS];
+    uint32_t scan_or[FC_MAIN_WARPS];
+    uint32_t firststar[FC_MAX_HUBS];          // epoch-keyed: lowest pending star bond of hub k
+    uint32_t span_min;
+    uint32_t bmin;                            // epoch-keyed: lowest blocked bond of the round
+    uint32_t star_epoch;
+    uint32_t wcnt[FC_MAIN_WARPS];             // pending bonds per main warp
+    uint32_t iu[32], iv[32], in[32];          // carried bonds, in order
+};
+static_assert(sizeof(FcShared) <= 320 + 768, "FcShared must fit the planner's reserve");
+
+#ifdef PZ_TIMING
+// clock read that waits for `dep` (a value produced by the operation being timed)
+__device__ __forceinline__ long long tm_now(uint32_t dep) {
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "r"(dep) : "memory");
+    return t;
+}
+#define FCT(...) __VA_ARGS__
+#else
+#define FCT(...)
+#endif
+
+template <class Store, int K>
+__global__ void __launch_bounds__(FC_ALL + 256, 1) sweep_fc_kernel(SweepArgs a, uint32_t store_bytes)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    using Rec = typename Store::Rec;
+    using Edge = typename Store::Edge;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool finder = tid >= FC_MAIN;
+    const bool carrier = warp == 0;
+    const int M = a.M;
+    const int clog = a.claim_log2;
+
+    uint32_t *claim = reinterpret_cast<uint32_t *>(smem);
+    const uint32_t claim_n = (1u << clog) - FC_NEW;
+    uint32_t *reps = claim + claim_n;                                          // [FC_NEW] ru | rv << 16
+    unsigned char *p = smem + (sizeof(uint32_t) << clog);
+    Store st;
+    st.bind(p, a, blockIdx.x);
+    FcShared *sh = reinterpret_cast<FcShared *>(p + store_bytes);
+
+    const Edge *edges = reinterpret_cast<const Edge *>(a.edges);
+    const bool spanning = a.sides2 != nullptr;
+    const int nb = (M + FC_NEW - 1) / FC_NEW;
+
+    for (int run = blockIdx.x; run < a.R; run += gridDim.x) {
+        st.init(tid, FC_ALL);
+        for (int i = tid; i < (int)claim_n; i += FC_ALL) claim[i] = CLAIM_FREE;
+        if (tid == 0) {
+            sh->span_min = NSPAN_NEVER;
+            sh->bmin = 0xffffffffu;
+            sh->star_epoch = 0xffffffffu;
+#pragma unroll
+            for (int k = 0; k < FC_MAX_HUBS; ++k) { sh->hubk[k] = 0ull; sh->firststar[k] = 0xffffffffu; }
+        }
+        __syncthreads();
+        const int32_t *perm = a.perms + (size_t)run * M;
+
+        if (finder) {
+            // ---- finder warps: FC_BPT bonds per thread and batch (as in sweep_fw_kernel) -------
+            const int ft = tid - FC_MAIN;
+            Edge uv_next[FC_BPT];
+            int32_t e_next[FC_BPT];
+#pragma unroll
+            for (int q = 0; q < FC_BPT; ++q) {
+                uv_next[q] = Edge(); e_next[q] = 0;
+                const int n = ft + q * FC_FIND;
+                if (n < M) uv_next[q] = __ldg(&edges[__ldcs(&perm[n])]);
+                if (n + FC_NEW < M) e_next[q] = __ldcs(&perm[n + FC_NEW]);
+            }
+            for (int b = 0; b < nb; ++b) {
+                uint32_t out[FC_BPT];
+#pragma unroll
+                for (int q = 0; q < FC_BPT; ++q) {
+                    const int n = b * FC_NEW + ft + q * FC_FIND;
+                    const Edge uv = uv_next[q];
+                    if (n + FC_NEW < M) uv_next[q] = __ldg(&edges[e_next[q]]);
+                    if (n + 2 * FC_NEW < M) e_next[q] = __ldcs(&perm[n + 2 * FC_NEW]);
+                    uint32_t u = 0, v = 0;
+                    if (n < M) {
+                        edge_uv(uv, u, v);
+                        uint32_t x[2] = {u, v};
+                        st.template find_rep_multi<2>(x);
+                        u = x[0]; v = x[1];
+                    }
+                    out[q] = u | (v << 16);
+                }
+                nb_sync(3, FC_PAIR);                    // the buffer of the previous batch has been read
+#pragma unroll
+                for (int q = 0; q < FC_BPT; ++q) reps[ft + q * FC_FIND] = out[q];
+                nb_arrive(2, FC_PAIR);                  // representatives of batch b are in the buffer
+            }
+        } else {
+            // ---- main warps ---------------------------------------------------------------------
+            Rec *rec_out = reinterpret_cast<Rec *>(a.recs) + (size_t)run * M;
+            bool track = spanning;                 // uniform over the main warps
+            uint32_t epoch = a.epoch_start;
+            if (nb > 0 && !carrier) nb_arrive(3, FC_PAIR);      // the buffer is free
+            // the bond this thread holds: a new thread one bond per batch, a carrier lane a carried one
+            uint32_t ru = 0, rv = 0, tu = 0, tv = 0;
+            int n = 0;
+            bool has = false, pending = false;
+            Rec rec = 0;
+            FCT(long long t_reps = 0, t_walk = 0, t_count = 0, t_round = 0, t_pack = 0, n_round = 0, n_star = 0, n_pack = 0, n_left = 0, t_star = 0;
+                const long long t_begin = tm_now(0);)
+            for (int b = 0; b < nb; ++b) {
+                const bool last = b + 1 == nb;
+                if (epoch < EPOCH_LOW) {           // rebase the claim epoch (see sweep_cta_kernel)
+                    nb_sync(1, FC_MAIN);
+                    for (int i = tid; i < (int)claim_n; i += FC_MAIN) claim[i] = CLAIM_FREE;
+                    if (tid == 0) {
+                        sh->star_epoch = 0xffffffffu; sh->bmin = 0xffffffffu;
+#pragma unroll
+                        for (int k = 0; k < FC_MAX_HUBS; ++k) sh->firststar[k] = 0xffffffffu;
+                    }
+                    epoch = a.epoch_start;
+                    nb_sync(1, FC_MAIN);
+                }
+                FCT(const long long tq0 = tm_now(0);)
+                if (!carrier) {
+                    n = b * FC_NEW + (tid - 32);
+                    has = n < M;
+                    nb_sync(2, FC_PAIR);
+                    const uint32_t rep = reps[tid - 32];
+                    FCT(t_reps += tm_now(rep) - tq0;)
+                    if (!last) nb_arrive(3, FC_PAIR);
+                    ru = rep & 0xffffu; rv = rep >> 16;
+                    rec = 0;
+                    pending = has;
+                }
+                FCT(const long long tq1 = tm_now(0);)
+                if (pending) {                      // up to the current roots
+                    st.find2(ru, rv, tu, tv);
+                    pending = ru != rv;
+                }
+                FCT(t_walk += tm_now(ru ^ rv) - tq1;)
+                bool carried_away = false;          // my bond moved to the carrier warp: it writes the record
+                int left = 0;
+                for (bool first = true;; first = false) {
+                    const uint32_t bal = __ballot_sync(0xffffffffu, pending);
+                    if (lane == 0) sh->wcnt[warp] = __popc(bal);
+                    // how many bonds are pending (the barrier also puts the merges of the previous
+                    // round in front of the walks below)
+                    FCT(const long long tq2 = tm_now(0);)
+                    left = nb_count(1, FC_MAIN, pending);
+                    FCT(const long long tq3 = tm_now((uint32_t)left); t_count += tq3 - tq2;)
+                    if (left == 0) break;
+                    if (left <= 32 && !last) {
+                        // ---- carry: pack the pending bonds, in order, into the carrier warp -------
+                        if (carrier && has && !pending) { __stcs(&rec_out[n], rec); has = false; }
+                        if (pending) {
+                            int base = 0;
+                            for (int w = 0; w < warp; ++w) base += (int)sh->wcnt[w];
+                            const int rank = base + __popc(bal & ((1u << lane) - 1u));
+                            sh->iu[rank] = ru; sh->iv[rank] = rv; sh->in[rank] = (uint32_t)n;
+                            carried_away = !carrier;
+                        }
+                        nb_sync(1, FC_MAIN);
+                        if (carrier) {
+                            has = pending = lane < left;
+                            rec = 0;
+                            if (has) { ru = sh->iu[lane]; rv = sh->iv[lane]; n = (int)sh->in[lane]; }
+                        } else {
+                            pending = false;
+                        }
+                        FCT(t_pack += tm_now(ru) - tq3; ++n_pack; n_left += left;)
+                        break;
+                    }
+                    if (!first && pending) {                        // walk up to the new roots
+                        st.find2(ru, rv, tu, tv);
+                        pending = ru != rv;
+                    }
+                    // ---- CTA round.  A warp without pending bonds only takes part in the barriers
+                    const bool warp_has = __any_sync(0xffffffffu, pending);
+                    const uint32_t key = (epoch << 10) | (uint32_t)tid;
+                    uint32_t hubroot = 0, o = 0, to = 0, th = 0, su = 0, sv = 0;
+                    int hu = -1, hv = -1, h = 0;
+                    unsigned long long hmin = ~0ull, hub0 = 0ull;   // smallest hub slot (candidates replace it)
+                    int kmin = 0;
+                    bool star = false;
+                    if (warp_has) {
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            const unsigned long long hk = sh->hubk[k];
+                            if (k == 0) hub0 = hk;
+                            if (hk < hmin) { hmin = hk; kmin = k; }
+                            if (hk != 0ull) {
+                                if (ru == (uint32_t)hk) hu = k;
+                                if (rv == (uint32_t)hk) hv = k;
+                            }
+                        }
+                        // star bond: exactly one side is a hub; o = the other root
+                        star = pending && ((hu >= 0) != (hv >= 0));
+                        h = hu >= 0 ? hu : hv;
+                        hubroot = hu >= 0 ? ru : rv;
+                        o = hu >= 0 ? rv : ru; to = hu >= 0 ? tv : tu;
+                        th = hu >= 0 ? tu : tv;
+                        if (pending) {
+                            su = claim_slot(star ? o : ru, clog);
+                            sv = claim_slot(star ? hubroot : rv, clog);
+                            if (su >= claim_n) su -= claim_n;
+                            if (sv >= claim_n) sv -= claim_n;
+                            atomicMin(&claim[su], key);
+                            if (!star) atomicMin(&claim[sv], key);
+                            else {
+                                if (K > 1) atomicMin(&sh->firststar[h], key);
+                                sh->star_epoch = epoch;             // this round needs the star barrier
+                            }
+                        }
+                    }
+                    nb_sync(1, FC_MAIN);                            // claims posted
+                    const bool star_round = sh->star_epoch == epoch;
+                    bool own = false;
+                    if (warp_has && pending) {
+                        const uint32_t cu = claim[su], cv = claim[sv];
+                        // a star bond owns its other root and no earlier bond claims its hub
+                        own = cu == key && (star ? (K == 1 || cv >= key) : cv == key);
+                        // a bond between two hubs waits for the earlier star bonds of both
+                        if (K > 1 && own && !star && hu >= 0)
+                            own = sh->firststar[hu] > key && sh->firststar[hv] > key;
+                        if (star_round && !own) atomicMin(&sh->bmin, key);
+                    }
+                    bool won = false;
+                    if (own && !star) {
+                        const uint32_t a1 = Store::size_m1(tu), b1 = Store::size_m1(tv);
+                        rec = make_rec<Rec>(a1, b1);
+                        const uint32_t sz = a1 + b1 + 2;
+                        const uint32_t m = st.unite(ru, tu, rv, tv, track);
+                        if (track && (m == 3u || a.any3)) atomicMin(&sh->span_min, (uint32_t)n + 1);
+                        const uint32_t big = a1 >= b1 ? ru : rv;
+                        const unsigned long long hk = ((unsigned long long)sz << 32) | big;
+                        if (hu >= 0) {                              // two hubs became one
+                            const int hb = a1 >= b1 ? hu : hv, hs = a1 >= b1 ? hv : hu;
+                            atomicMax(&sh->hubk[hb], hk);
+                            sh->hubk[hs] = 0ull;
+                        } else if (hk > hmin && (kmin == 0 || sz >= PZ_HUB_MIN)) {
+                            atomicMax(&sh->hubk[kmin], hk);
+                        } else if (K > 1 && hk > hub0) {            // too small for a secondary hub: slot 0 takes any size
+                            atomicMax(&sh->hubk[0], hk);
+                        }
+                        won = true;
+                    }
+                    int nstar = 0;
+                    if (star_round) nstar = nb_count(1, FC_MAIN, own && star);
+                    if (nstar) {
+                        // star bonds merge together iff no earlier bond is blocked
+                        const bool sw = own && star && key < sh->bmin;
+                        unsigned long long v = 0ull, incl = 0ull;
+                        uint32_t sb = 0u, sincl = 0u, sexcl = 0u;
+                        if (__any_sync(0xffffffffu, sw)) {
+                            if (sw) {
+                                v = (unsigned long long)(Store::size_m1(to) + 1) << (21 * h);
+                                if (track) sb = st.sides_of_root(o, to) << (2 * h);
+                            }
+                            incl = v; sincl = sb;
+#pragma unroll
+                            for (int k = 1; k < 32; k <<= 1) {
+                                const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, k);
+                                const uint32_t t2 = __shfl_up_sync(0xffffffffu, sincl, k);
+                                if (lane >= k) { incl += t; sincl |= t2; }
+                            }
+                            sexcl = __shfl_up_sync(0xffffffffu, sincl, 1);
+                            if (lane == 0) sexcl = 0u;
+                        }
+                        if (lane == 31) { sh->scan_tot[warp] = incl; sh->scan_or[warp] = sincl; }
+                        nb_sync(1, FC_MAIN);
+                        if (sw) {
+                            unsigned long long pre = incl - v, total = 0ull;
+                            uint32_t spre = sexcl, stot = 0u;
+#pragma unroll
+                            for (int w = 0; w < FC_MAIN_WARPS; ++w) {
+                                const unsigned long long t = sh->scan_tot[w];
+                                const uint32_t t2 = sh->scan_or[w];
+                                if (w < warp) { pre += t; spre |= t2; }
+                                total += t; stot |= t2;
+                            }
+                            const uint32_t hub_m1 = Store::size_m1(th);     // hub size - 1 at round start
+                            const uint32_t pre_sz = (uint32_t)(pre >> (21 * h)) & 0x1fffffu;
+                            rec = make_rec<Rec>(Store::size_m1(to), hub_m1 + pre_sz);
+                            st.make_child(o, hubroot);
+                            if (track) {
+                                const uint32_t m = st.sides_of_root(hubroot, th) |
+                                                   (((spre | sb) >> (2 * h)) & 3u);
+                                if (m == 3u || a.any3) atomicMin(&sh->span_min, (uint32_t)n + 1);
+                            }
+                            if (pre_sz == 0) {      // first star bond of its hub in this round: publish the hub
+                                const uint32_t tot_sz = (uint32_t)(total >> (21 * h)) & 0x1fffffu;
+                                st.set_root(hubroot, hub_m1 + tot_sz, track ? ((stot >> (2 * h)) & 3u) : 0u);
+                                const unsigned long long nk = ((unsigned long long)(hub_m1 + tot_sz + 1) << 32) | hubroot;
+                                if (nk > sh->hubk[h]) sh->hubk[h] = nk;
+                            }
+                            won = true;
+                        }
+                    }
+                    if (won) pending = false;
+                    --epoch;
+                    FCT(t_round += tm_now((uint32_t)rec) - tq3; ++n_round; if (nstar) ++n_star;)
+                }
+                // spanning is decided once no earlier bond can still join the two sides
+                if (track && left == 0 && sh->span_min != NSPAN_NEVER) track = false;
+                if (carrier) {
+                    if (has && !pending) { __stcs(&rec_out[n], rec); has = false; }
+                } else if (has && !carried_away) {
+                    __stcs(&rec_out[n], rec);
+                }
+            }
+            FCT(if ((lane == 0) && (warp == 0 || warp == 1 || warp == 9) && blockIdx.x == 3 && run < 2 * (int)gridDim.x)
+                    printf("fc run %d warp %2d: total %lld | reps %lld | walk %lld | count barriers %lld | %lld rounds (%lld star) %lld cycles | %lld packs (%lld bonds) %lld cycles\n",
+                           run, warp, tm_now(0) - t_begin, t_reps, t_walk, t_count, n_round, n_star, t_round, n_pack, n_left, t_pack);)
+        }
+        __syncthreads();
+        if (tid == 0) a.nspan[run] = sh->span_min;
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
 // planning and launch
 // ---------------------------------------------------------------------------
 
@@ -1196,10 +1555,10 @@ static SweepPlan plan_team(SweepPlan p, int32_t N, int32_t R, int sms, size_t sm
     // while the main warps run the rounds (PZ_FINDERS=0 switches them off)
     p.finders = 0;
     if (p.kind == STORE_S16B && CTA_WARPS == 16) {
-        int want = 1;
+        int want = 1;           // 0: lock step, 1: finder warps + tail mode, 2: finder warps + carried bonds + hubs
         if (const char *e = getenv("PZ_FINDERS")) want = atoi(e);
         if (want && clog >= 11 && align16h(fixed + ((size_t)4 << clog) + 768) <= smem_optin) {
-            p.finders = 1;      // (the hand-over buffer is carved out of the claim table)
+            p.finders = want;   // (the hand-over buffer is carved out of the claim table)
             p.smem_bytes = align16h(fixed + ((size_t)4 << clog) + 768);      // + TailShared
         }
     }
@@ -1326,6 +1685,15 @@ static cudaError_t launch_t(const SweepPlan &p, const SweepArgs &a, cudaStream_t
 
 cudaError_t launch_sweep(const SweepPlan &p, const SweepArgs &a, cudaStream_t s)
 {
+    if (p.team && p.finders >= 2) {
+        static const int hubs = getenv("PZ_HUBS") ? atoi(getenv("PZ_HUBS")) : 2;
+        auto kern = hubs <= 1 ? sweep_fc_kernel<StoreS16BF, 1> : hubs == 2 ? sweep_fc_kernel<StoreS16BF, 2>
+                                                                           : sweep_fc_kernel<StoreS16BF, 3>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
+        if (e != cudaSuccess) return e;
+        kern<<<p.grid, FC_ALL, p.smem_bytes, s>>>(a, (uint32_t)p.store_bytes);
+        return cudaGetLastError();
+    }
     if (p.team && p.finders) {
         cudaError_t e = cudaFuncSetAttribute(sweep_fw_kernel<StoreS16BF>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);

@@ -642,6 +642,51 @@ def test_finder_warps_match_lock_step_kernel(L, runs):
     assert np.array_equal(got["0"][1][1], got["1"][1][1]) and np.array_equal(got["0"][1][2], got["1"][1][2])
 
 
+@pytest.mark.parametrize("L,runs,hubs,epoch", [(256, 2500, 2, None), (256, 1500, 1, None), (256, 1500, 3, None),
+                                               (200, 1500, 2, None), (182, 1200, 3, None),
+                                               (256, 600, 2, 0x1300)])
+def test_carried_bonds_and_hubs_match_lock_step_kernel(L, runs, hubs, epoch):
+    """sweep_fc_kernel (PZ_FINDERS=2, the default for one run per SM): pending bonds carried into the
+    next batch, star merging around PZ_HUBS hubs.  Thousands of full runs must give exactly the
+    sums, canonical partials and first-spanning counts of the plain lock-step kernel, and the first
+    runs the oracle's rows; a short claim epoch exercises the rebase."""
+    from pypercolate_b200 import lowering
+    from oracle import oracle
+    n = _native()
+    g = lowering.lowered_spanning_2d_grid(L)
+    N, M = g.num_nodes, g.num_edges
+    seeds = np.arange(runs, dtype=np.uint32) * 104729 + 71
+    ps = np.linspace(0.45, 0.55, 7)
+    got = {}
+    for finders in ("0", "2"):
+        over = {"PZ_FINDERS": finders, "PZ_HUBS": str(hubs)}
+        if epoch is not None and finders == "2":
+            over["PZ_EPOCH_START"] = str(epoch)
+        old = {k: os.environ.get(k) for k in over}
+        os.environ.update(over)
+        try:
+            ctx = n.Context(0)
+            ctx.set_graph(g)
+            ctx.set_ps(ps)
+            ctx.run_fused(runs, n.PERM_FEISTEL, seeds, n.FUSE_MICRO | n.FUSE_CANON)
+            got[finders] = (ctx.micro_export(), ctx.canon_export())
+            if finders == "2":
+                rows, perms = ctx.run_rows(4, n.PERM_FEISTEL, seeds[:4], want_perms=True)
+                for r in range(4):
+                    ref = oracle.sweep_rows(N, M, g.eu, g.ev, g.side_mask, False, perms[r])
+                    assert_rows_equal(rows[r], ref, "carried bonds L=%d hubs=%d" % (L, hubs))
+            ctx.close()
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+    assert np.array_equal(acc_totals(got["0"][0]), acc_totals(got["2"][0]))
+    assert got["0"][1][0] == got["2"][1][0]
+    assert np.array_equal(got["0"][1][1], got["2"][1][1]) and np.array_equal(got["0"][1][2], got["2"][1][2])
+
+
 def test_finder_warps_on_sparse_and_empty_graphs():
     """The one-run-per-SM shape (32768 < N <= 65536) on graphs that are not lattices: no bonds at
     all, fewer bonds than one batch, a long chain, a random sparse graph."""
