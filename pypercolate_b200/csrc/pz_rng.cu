@@ -104,8 +104,8 @@ __device__ __forceinline__ uint32_t philox_bounded(uint32_t seed, uint32_t bucke
 
 struct PhiloxPlan {
     int log2_buckets;
-    int cap;             // shared-memory capacity (entries) of one bucket in the shuffle phase
-    int fy_threads;
+    int slab_buckets;    // buckets shuffled together in shared memory (one thread each)
+    int slab_cap;        // entries the slab buffer holds
     size_t smem_bytes;
 };
 
@@ -115,33 +115,36 @@ static PhiloxPlan plan_philox(int32_t M)
     int lb = 0;
     while (lb < 11 && ((long long)64 << lb) < M) ++lb;      // mean bucket ~64 until B = 2048
     p.log2_buckets = lb;
-    const double mean = (double)M / (double)(1 << lb);
-    int cap = (int)(mean + 8.0 * sqrt(mean) + 16.0);
-    cap |= 1;                                               // odd stride: no systematic bank conflicts
-    // the shuffle buffers reuse the space of the per-warp histograms, so that
-    // three CTAs fit one SM (occupancy matters more than shuffle threads)
-    const size_t hist = (size_t)PH_WARPS * ((size_t)1 << lb) * 4;
-    size_t budget = hist > (size_t)32 * 1024 ? hist : (size_t)32 * 1024;
-    int t = (int)(budget / ((size_t)cap * 4));
-    if (t > PH_THREADS) t = PH_THREADS;
-    if (t < 1) t = 1;
-    p.cap = cap;
-    p.fy_threads = t;
-    const size_t fy = (size_t)t * cap * 4;
-    p.smem_bytes = (hist > fy ? hist : fy) + ((size_t)(1 << lb) + 1) * 4 + 64;
+    const int B = 1 << lb;
+    const double mean = (double)M / (double)B;
+    // the slab buffer reuses the space of the per-warp histograms (never less than 64 KB of it)
+    const size_t hist = (size_t)PH_WARPS * (size_t)B * 4;
+    static const size_t slab_kb = getenv("PZ_PHILOX_SLAB_KB") ? (size_t)atoi(getenv("PZ_PHILOX_SLAB_KB")) : 72;
+    const size_t budget = hist > slab_kb * 1024 ? hist : slab_kb * 1024;
+    // as many buckets per slab as threads, fewer when the buckets are large: S mean + 8 sigma + slack
+    int S = B < PH_THREADS ? B : PH_THREADS;
+    auto need = [&](int k) { return (size_t)((double)k * mean + 8.0 * sqrt((double)k * mean) + 64.0); };
+    while (S > 1 && need(S) * 4 > budget) S >>= 1;
+    p.slab_buckets = S;
+    size_t cap = need(S);
+    if (cap * 4 < budget) cap = budget / 4;                 // use what is there anyway
+    if (cap * 4 > (size_t)160 * 1024) cap = (size_t)160 * 1024 / 4;     // (huge buckets take the global path)
+    p.slab_cap = (int)cap;
+    const size_t slab = cap * 4;
+    p.smem_bytes = (hist > slab ? hist : slab) + ((size_t)B + 1) * 4 + 64;
     return p;
 }
 
 __global__ void __launch_bounds__(PH_THREADS) perm_philox_kernel(int32_t M, int32_t R,
                                                                   const uint32_t *seeds, int32_t *perms,
-                                                                  int log2b, int cap, int fy_threads)
+                                                                  int log2b, int slab_buckets, int slab_cap)
 {
     extern __shared__ __align__(16) uint32_t sm[];
     const int B = 1 << log2b;
     const uint32_t bmask = (uint32_t)B - 1u;
     uint32_t *start = sm;                       // [B + 1]
     uint32_t *hist = sm + B + 1;                // [PH_WARPS][B] then per-warp bases
-    uint32_t *fybuf = sm + B + 1;               // [fy_threads][cap]   (after the scatter)
+    uint32_t *slab = sm + B + 1;                // [slab_cap]   (after the scatter)
     __shared__ uint32_t scan_tot[PH_WARPS];
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -212,15 +215,23 @@ __global__ void __launch_bounds__(PH_THREADS) perm_philox_kernel(int32_t M, int3
         }
         __syncthreads();
 
-        // ---- C: Fisher-Yates inside every bucket, in shared memory -------------
-        for (int b0 = 0; b0 < B; b0 += fy_threads) {
+        // ---- C: Fisher-Yates inside every bucket, in shared memory.  The buckets of a slab are
+        // contiguous in the output row: the CTA copies the slab in (coalesced), every thread
+        // restores the ascending bond order of its bucket and shuffles it, the CTA copies it back.
+        for (int b0 = 0; b0 < B; b0 += slab_buckets) {
+            const int b1 = min(B, b0 + slab_buckets);
+            const uint32_t lo = start[b0], n = start[b1] - lo;
+            const bool staged = n <= (uint32_t)slab_cap;      // CTA-uniform
+            if (staged) {
+                for (uint32_t k = t; k < n; k += PH_THREADS) slab[k] = (uint32_t)out[lo + k];
+                __syncthreads();
+            }
             const int b = b0 + t;
-            if (t < fy_threads && b < B) {
+            if (b < b1) {
                 const uint32_t s0 = start[b], sz = start[b + 1] - s0;
                 if (sz > 1) {
-                    if ((int)sz <= cap) {
-                        uint32_t *buf = fybuf + (size_t)t * cap;
-                        for (uint32_t k = 0; k < sz; ++k) buf[k] = (uint32_t)out[s0 + k];
+                    if (staged) {
+                        uint32_t *buf = slab + (s0 - lo);
                         for (uint32_t k = 1; k < sz; ++k) {       // restore ascending bond order
                             const uint32_t v = buf[k];
                             uint32_t j = k;
@@ -233,8 +244,7 @@ __global__ void __launch_bounds__(PH_THREADS) perm_philox_kernel(int32_t M, int3
                             const uint32_t a = buf[k], c = buf[j];
                             buf[k] = c; buf[j] = a;
                         }
-                        for (uint32_t k = 0; k < sz; ++k) out[s0 + k] = (int32_t)buf[k];
-                    } else {                      // over-full bucket: same sort + shuffle in place
+                    } else {                      // a slab too large for shared memory: same sort + shuffle in place
                         for (uint32_t k = 1; k < sz; ++k) {
                             const int32_t v = out[s0 + k];
                             uint32_t j = k;
@@ -250,8 +260,12 @@ __global__ void __launch_bounds__(PH_THREADS) perm_philox_kernel(int32_t M, int3
                     }
                 }
             }
+            if (staged) {
+                __syncthreads();
+                for (uint32_t k = t; k < n; k += PH_THREADS) out[lo + k] = (int32_t)slab[k];
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
 
@@ -265,8 +279,8 @@ cudaError_t launch_perm_philox(int32_t M, int32_t R, const uint32_t *seeds, int3
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)p.smem_bytes);
     if (e != cudaSuccess) return e;
-    perm_philox_kernel<<<R, PH_THREADS, p.smem_bytes, s>>>(M, R, seeds, perms, p.log2_buckets, p.cap,
-                                                           p.fy_threads);
+    perm_philox_kernel<<<R, PH_THREADS, p.smem_bytes, s>>>(M, R, seeds, perms, p.log2_buckets,
+                                                           p.slab_buckets, p.slab_cap);
     *launches = 1;
     return cudaGetLastError();
 }

@@ -1,8 +1,9 @@
+"""Whole fused step per bond-order generator (argv) under PZ_PIPELINE / PZ_FINDERS / ... from the environment; RUNS=n."""
 import sys, os, time
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch
 from pypercolate_b200 import _native, lowering
-runs = 20000
+runs = int(os.environ.get('RUNS', '20000'))
 g = lowering.lowered_spanning_2d_grid(256); M = g.num_edges
 ctx = _native.context_for(g, 0); ctx.set_ps(np.linspace(0.45, 0.55, 100))
 seeds = (np.arange(runs, dtype=np.uint64) * 2654435761 % 2 ** 32).astype(np.uint32)
