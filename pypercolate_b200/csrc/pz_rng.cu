@@ -102,6 +102,25 @@ __device__ __forceinline__ uint32_t philox_bounded(uint32_t seed, uint32_t bucke
     }
 }
 
+// the same draw from the word already selected (callers that evaluate the groups themselves)
+__device__ __forceinline__ uint32_t philox_bounded_w(uint32_t seed, uint32_t bucket, uint32_t k, uint32_t w)
+{
+    const uint32_t range = k + 1u;
+    uint64_t m = (uint64_t)w * range;
+    if ((uint32_t)m >= range) return (uint32_t)(m >> 32);
+    const uint32_t thresh = (0u - range) % range;
+    if ((uint32_t)m >= thresh) return (uint32_t)(m >> 32);
+    for (uint32_t attempt = 1;; ++attempt) {
+        uint32_t r[4];
+        philox4x32_10(seed, PHILOX_KEY1, k, bucket, attempt, 2u, r);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            m = (uint64_t)r[q] * range;
+            if ((uint32_t)m >= thresh) return (uint32_t)(m >> 32);
+        }
+    }
+}
+
 struct PhiloxPlan {
     int log2_buckets;
     int slab_buckets;    // buckets shuffled together in shared memory (one thread each)
@@ -269,11 +288,219 @@ __global__ void __launch_bounds__(PH_THREADS) perm_philox_kernel(int32_t M, int3
     }
 }
 
+// ---------------------------------------------------------------------------
+// The same permutation in two levels (M <= 131072, i.e. up to the L = 256 square lattice).
+// perm_philox_kernel scatters every bond to its bucket in global memory, one 4-byte store per
+// bond to 2048 places: with several hundred runs in flight the half-written sectors do not
+// survive in the L2, and the kernel is bound by that read-modify-write traffic to DRAM.  Here
+// the bucket number is split: its high bits name one of at most 16 SUPER-buckets, its low 7 bits
+// a bucket inside it.
+//   A  histogram of the bucket draws (bucket starts), per-warp counts of the super-buckets;
+//   B  every warp appends its bonds, in order, to its own segment of each super-bucket: 16
+//      sequential streams per warp, whose sectors fill within a few iterations and combine in
+//      the L2.  An entry carries its bucket: bond | low bits << 17;
+//   C  per super-bucket (about 8160 entries): per-warp counts of the 128 buckets, then a stable
+//      placement into shared memory in almost ascending order (warp after warp; only the entries
+//      of one warp instruction may swap), one thread per bucket restores the ascending bond order
+//      -- which makes the result independent of timing -- and shuffles
+//      it (Fisher-Yates, Philox draws), and the CTA writes the super-bucket out, coalesced.
+// DRAM traffic: about 16 bytes per bond, all of it sequential.
+// ---------------------------------------------------------------------------
+static constexpr int PH2_SUB_LOG_MAX = 7;
+
+struct Philox2Plan {
+    int log2_buckets, sub_log, supers;
+    int super_cap;
+    size_t smem_bytes;
+};
+
+static Philox2Plan plan_philox2(int32_t M)
+{
+    Philox2Plan p{};
+    int lb = 0;
+    while (lb < 11 && ((long long)64 << lb) < M) ++lb;
+    p.log2_buckets = lb;
+    p.sub_log = lb < PH2_SUB_LOG_MAX ? lb : PH2_SUB_LOG_MAX;
+    p.supers = 1 << (lb - p.sub_log);
+    const double mean = (double)M / (double)p.supers;
+    p.super_cap = p.supers == 1 ? std::max(M, 1) : (int)(mean + 10.0 * sqrt(mean) + 64.0);
+    const size_t B = (size_t)1 << lb;
+    p.smem_bytes = (B + 1) * 4 + (size_t)PH_WARPS * (p.supers + 1) * 4 +
+                   (size_t)PH_WARPS * ((size_t)1 << p.sub_log) * 4 + (size_t)p.super_cap * 4 + 64;
+    return p;
+}
+
+__global__ void __launch_bounds__(PH_THREADS) perm_philox2_kernel(int32_t M, int32_t R, const uint32_t *seeds,
+                                                                   int32_t *perms, int log2b, int sub_log,
+                                                                   int super_cap)
+{
+    extern __shared__ __align__(16) uint32_t sm[];
+    const int B = 1 << log2b;
+    const uint32_t bmask = (uint32_t)B - 1u;
+    const int NSUB = 1 << sub_log, SB = B >> sub_log;
+    uint32_t *start = sm;                               // [B + 1]  counts, then bucket starts
+    uint32_t *wsuper = start + B + 1;                   // [PH_WARPS][SB]  counts, then the warps' append positions
+    uint32_t *wsub = wsuper + PH_WARPS * (SB + 1);      // [PH_WARPS][NSUB]
+    uint32_t *buf = wsub + PH_WARPS * NSUB;             // [super_cap]
+    __shared__ uint32_t scan_tot[PH_WARPS];
+
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int per_warp = (((M + PH_WARPS - 1) / PH_WARPS) + 127) & ~127;
+    const int w_lo = min(M, warp * per_warp), w_hi = min(M, w_lo + per_warp);
+
+    for (int run = blockIdx.x; run < R; run += gridDim.x) {
+        const uint32_t seed = seeds[run];
+        int32_t *out = perms + (size_t)run * M;
+
+        // ---- A: bucket counts, per-warp super-bucket counts -------------------------------
+        for (int i = t; i < B + 1 + PH_WARPS * (SB + 1); i += PH_THREADS) sm[i] = 0;
+        __syncthreads();
+        for (int i0 = w_lo + 4 * lane; i0 < w_hi; i0 += 128) {
+            uint32_t o[4];
+            philox_buckets4(seed, (uint32_t)i0 >> 2, o);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (i0 + q < w_hi) {
+                    const uint32_t b = o[q] & bmask;
+                    atomicAdd(&start[b], 1u);
+                    atomicAdd(&wsuper[warp * (SB + 1) + (b >> sub_log)], 1u);
+                }
+        }
+        __syncthreads();
+        {
+            // exclusive scan of the bucket counts: thread t owns buckets [t*per, (t+1)*per)
+            const int per = (B + PH_THREADS - 1) / PH_THREADS;
+            const int b_lo = min(B, t * per), b_hi = min(B, b_lo + per);
+            uint32_t mine = 0;
+            for (int b = b_lo; b < b_hi; ++b) mine += start[b];
+            uint32_t incl = mine;
+            for (int k = 1; k < 32; k <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, k);
+                if (lane >= k) incl += o;
+            }
+            if (lane == 31) scan_tot[warp] = incl;
+            __syncthreads();
+            uint32_t pre = incl - mine;
+            for (int w = 0; w < warp; ++w) pre += scan_tot[w];
+            for (int b = b_lo; b < b_hi; ++b) { const uint32_t c = start[b]; start[b] = pre; pre += c; }
+            if (t == PH_THREADS - 1) start[B] = (uint32_t)M;
+        }
+        __syncthreads();
+        if (t < SB) {
+            // warp w appends to super-bucket t behind the warps before it
+            uint32_t pos = start[t << sub_log];
+            for (int w = 0; w < PH_WARPS; ++w) {
+                const uint32_t c = wsuper[w * (SB + 1) + t];
+                wsuper[w * (SB + 1) + t] = pos;
+                pos += c;
+            }
+        }
+        __syncthreads();
+
+        // ---- B: append every bond to its warp's segment of its super-bucket ------------------
+        for (int blk = w_lo; blk < w_hi; blk += 128) {
+            uint32_t o[4];
+            philox_buckets4(seed, (uint32_t)(blk + 4 * lane) >> 2, o);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int i = blk + 4 * lane + q;
+                const uint32_t b = o[q] & bmask, sp = b >> sub_log;
+                // (two bonds of one warp instruction that share a super-bucket may land in either
+                // order: phase C sorts every bucket, so the result does not depend on it)
+                if (i < w_hi)
+                    out[atomicAdd(&wsuper[warp * (SB + 1) + sp], 1u)] =
+                        (int32_t)((uint32_t)i | ((b & (NSUB - 1)) << 17));
+            }
+        }
+        __syncthreads();
+
+        // ---- C: super-bucket by super-bucket ----------------------------------------------------
+        for (int sp = 0; sp < SB; ++sp) {
+            const uint32_t lo = start[sp << sub_log], n = start[(sp + 1) << sub_log] - lo;
+            if (n > (uint32_t)super_cap) __trap();       // (ten standard deviations above the mean)
+            // per-warp counts of the buckets: warp w owns the entries [w*ch, (w+1)*ch) of the super-bucket
+            const uint32_t ch = ((n + PH_WARPS - 1) / PH_WARPS + 31u) & ~31u;
+            const uint32_t c_lo = min(n, warp * ch), c_hi = min(n, c_lo + ch);
+            for (int i = t; i < PH_WARPS * NSUB; i += PH_THREADS) wsub[i] = 0;
+            __syncthreads();
+            for (uint32_t k = c_lo + lane; k < c_hi; k += 32)
+                atomicAdd(&wsub[warp * NSUB + ((uint32_t)out[lo + k] >> 17)], 1u);
+            __syncthreads();
+            if (t < NSUB) {
+                uint32_t pos = start[(sp << sub_log) + t] - lo;
+                for (int w = 0; w < PH_WARPS; ++w) {
+                    const uint32_t c = wsub[w * NSUB + t];
+                    wsub[w * NSUB + t] = pos;
+                    pos += c;
+                }
+            }
+            __syncthreads();
+            // placement: warps by their bases, the entries of one warp instruction in any order
+            uint32_t v_next = c_lo + lane < c_hi ? (uint32_t)out[lo + c_lo + lane] : 0u;
+            for (uint32_t k0 = c_lo; k0 < c_hi; k0 += 32) {
+                const uint32_t k = k0 + lane;
+                const bool ok = k < c_hi;
+                const uint32_t v = v_next;
+                if (k + 32 < c_hi) v_next = (uint32_t)out[lo + k + 32];     // the next step's load is in flight
+                if (ok) buf[atomicAdd(&wsub[warp * NSUB + (v >> 17)], 1u)] = v & 0x1ffffu;
+            }
+            __syncthreads();
+            if (t < NSUB) {
+                const int b = (sp << sub_log) + t;
+                const uint32_t s0 = start[b] - lo, sz = start[b + 1] - start[b];
+                if (sz > 1) {
+                    uint32_t *x = buf + s0;
+                    for (uint32_t k = 1; k < sz; ++k) {       // restore ascending bond order
+                        const uint32_t v = x[k];
+                        uint32_t j = k;
+                        while (j > 0 && x[j - 1] > v) { x[j] = x[j - 1]; --j; }
+                        x[j] = v;
+                    }
+                }
+                // the lanes of a warp walk k together from the largest bucket down: then all of them
+                // reach a new group of four draws (one Philox call) in the same iteration -- with a
+                // private k per lane some lane needs a call in nearly every iteration
+                uint32_t *x = buf + s0;
+                const uint32_t kmax = __reduce_max_sync(__activemask(), sz);
+                uint32_t o[4] = {0u, 0u, 0u, 0u};
+                for (uint32_t k = kmax - 1; k >= 1 && kmax > 1; --k) {
+                    if (((k & 3u) == 3u || k == kmax - 1) && (k & ~3u) < sz)
+                        philox4x32_10(seed, PHILOX_KEY1, k >> 2, (uint32_t)b, 0u, 1u, o);
+                    if (k < sz) {
+                        const uint32_t w = (k & 2u) ? ((k & 1u) ? o[3] : o[2]) : ((k & 1u) ? o[1] : o[0]);
+                        const uint32_t j = philox_bounded_w(seed, (uint32_t)b, k, w);
+                        const uint32_t a = x[k], c = x[j];
+                        x[k] = c; x[j] = a;
+                    }
+                }
+            }
+            __syncthreads();
+            for (uint32_t k = t; k < n; k += PH_THREADS) out[lo + k] = (int32_t)buf[k];
+            __syncthreads();
+        }
+    }
+}
+
 cudaError_t launch_perm_philox(int32_t M, int32_t R, const uint32_t *seeds, int32_t *perms,
                                cudaStream_t s, int *launches)
 {
     *launches = 0;
     if (R <= 0 || M <= 0) return cudaSuccess;
+    static const bool two_level = !(getenv("PZ_PHILOX_TWO_LEVEL") && atoi(getenv("PZ_PHILOX_TWO_LEVEL")) == 0);
+    if (two_level && M <= 131072) {
+        const Philox2Plan p = plan_philox2(M);
+        cudaError_t e = cudaFuncSetAttribute(perm_philox2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)p.smem_bytes);
+        if (e != cudaSuccess) return e;
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int grid = std::min(R, sms * 8);
+        perm_philox2_kernel<<<grid, PH_THREADS, p.smem_bytes, s>>>(M, R, seeds, perms, p.log2_buckets, p.sub_log,
+                                                                   p.super_cap);
+        *launches = 1;
+        return cudaGetLastError();
+    }
     const PhiloxPlan p = plan_philox(M);
     cudaError_t e = cudaFuncSetAttribute(perm_philox_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -629,15 +856,22 @@ __global__ void __launch_bounds__(32 * WP_WARPS, 4) perm_warp_kernel(int32_t M, 
     }
 }
 
-// Shape of a launch: one CTA per SM (it has to fit next to a sweep CTA), PZ_WP_WARPS warps each
-// (default 4); every warp owns one staging row.  Few warps keep the staging rows inside the L2.
+// Shape of a launch: PZ_WP_CTAS CTAs per SM (default 2; next to a sweep CTA one of them is resident
+// at a time), PZ_WP_WARPS warps each (default 8); every warp owns one staging row.  Measured on one
+// B200 (profiles/rng_r2.txt): the shuffle saturates at about 1200 warps (2.2e10 bonds/s, bound by
+// the random sector traffic of the staging rows); large graphs take fewer warps so that the
+// staging rows stay below 2 GB.
 void perm_warp_shape(int sms, int32_t M, int *ctas, int *wpc, size_t *stride)
 {
-    static const int per_sm = getenv("PZ_WP_CTAS") ? std::max(1, atoi(getenv("PZ_WP_CTAS"))) : 1;
-    static const int w = getenv("PZ_WP_WARPS") ? std::min(WP_WARPS, std::max(1, atoi(getenv("PZ_WP_WARPS")))) : 4;
+    static const int per_sm = getenv("PZ_WP_CTAS") ? std::max(1, atoi(getenv("PZ_WP_CTAS"))) : 2;
+    static const int w = getenv("PZ_WP_WARPS") ? std::min(WP_WARPS, std::max(1, atoi(getenv("PZ_WP_WARPS")))) : 8;
     *ctas = sms * per_sm;
     *wpc = w;
     *stride = ((size_t)std::max(M, 1) + 31) / 32 * 32;
+    const size_t budget = (size_t)2 << 30;
+    while (*wpc > 1 && (size_t)*ctas * *wpc * *stride * 4 > budget) *wpc >>= 1;
+    while (*ctas > sms && (size_t)*ctas * *wpc * *stride * 4 > budget) *ctas -= sms;
+    while (*ctas > 1 && (size_t)*ctas * *wpc * *stride * 4 > budget) *ctas >>= 1;
 }
 
 size_t perm_stage_ints(int sms, int32_t M)
