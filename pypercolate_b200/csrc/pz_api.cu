@@ -672,7 +672,8 @@ int pz_run_fused(pz_ctx *c, int32_t R, int perm_mode, const void *perm_src, int 
     const int P = c->num_p;
     const int pipeline = (base_mode == PZ_PERM_HOST || base_mode == PZ_PERM_DEVICE) ? 0
                          : c->pipeline >= 0 ? c->pipeline
-                         : (base_mode == PZ_PERM_PHILOX ? 0 : 2);     // (the bucketed shuffle needs shared memory)
+                         : 2;     // (the bucketed Philox shuffle needs shared memory: its CTAs follow the
+                                  //  sweep's as those retire and run next to the statistics kernels)
     // three slots rotate even on one stream: the host then runs up to two chunks ahead of the
     // device instead of waiting for every chunk's statistics before it launches the next sweep
     const int nslot = pz_ctx::PZ_SLOTS;

@@ -20,7 +20,8 @@
 //    Counters: bucket draws (i >> 2, 0, 0, 0) word i & 3; Fisher-Yates draw of
 //    step k of bucket b: word k & 3 of (k >> 2, b, 0, 1), on the (rare) Lemire
 //    rejection words 0.. of (k, b, attempt >= 1, 2).  Key: (seed, 0x50455243).
-//    Every Philox call therefore serves four bonds.
+//    Every Philox call therefore serves four bonds.  (B grows with M up to 2^17: the mean bucket
+//    stays near 64 bonds; M <= 2^24.)
 //    oracle/pz_oracle.c restates this algorithm on the CPU for bit-exact tests.
 //
 //  * perm_feistel: the bond order as a keyed BIJECTION of [0, M): position n ->
@@ -76,33 +77,8 @@ __device__ __forceinline__ void philox_buckets4(uint32_t seed, uint32_t g, uint3
     philox4x32_10(seed, PHILOX_KEY1, g, 0u, 0u, 0u, o);
 }
 
-// unbiased j in [0, k] (Lemire).  `o` caches the four words of counter
-// (k >> 2, bucket, 0, 1); `grp` is the group they belong to.
-__device__ __forceinline__ uint32_t philox_bounded(uint32_t seed, uint32_t bucket, uint32_t k,
-                                                   uint32_t (&o)[4], uint32_t &grp)
-{
-    const uint32_t range = k + 1u;
-    if ((k >> 2) != grp) {
-        grp = k >> 2;
-        philox4x32_10(seed, PHILOX_KEY1, grp, bucket, 0u, 1u, o);
-    }
-    const uint32_t w = (k & 2u) ? ((k & 1u) ? o[3] : o[2]) : ((k & 1u) ? o[1] : o[0]);
-    uint64_t m = (uint64_t)w * range;
-    if ((uint32_t)m >= range) return (uint32_t)(m >> 32);      // cannot be below the threshold
-    const uint32_t thresh = (0u - range) % range;
-    if ((uint32_t)m >= thresh) return (uint32_t)(m >> 32);
-    for (uint32_t attempt = 1;; ++attempt) {
-        uint32_t r[4];
-        philox4x32_10(seed, PHILOX_KEY1, k, bucket, attempt, 2u, r);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            m = (uint64_t)r[q] * range;
-            if ((uint32_t)m >= thresh) return (uint32_t)(m >> 32);
-        }
-    }
-}
-
-// the same draw from the word already selected (callers that evaluate the groups themselves)
+// unbiased j in [0, k] (Lemire) from word k & 3 of counter (k >> 2, bucket, 0, 1), which the caller
+// has selected; on the (rare) rejection words 0.. of (k, bucket, attempt >= 1, 2)
 __device__ __forceinline__ uint32_t philox_bounded_w(uint32_t seed, uint32_t bucket, uint32_t k, uint32_t w)
 {
     const uint32_t range = k + 1u;
@@ -121,192 +97,27 @@ __device__ __forceinline__ uint32_t philox_bounded_w(uint32_t seed, uint32_t buc
     }
 }
 
-struct PhiloxPlan {
-    int log2_buckets;
-    int slab_buckets;    // buckets shuffled together in shared memory (one thread each)
-    int slab_cap;        // entries the slab buffer holds
-    size_t smem_bytes;
-};
-
-static PhiloxPlan plan_philox(int32_t M)
-{
-    PhiloxPlan p{};
-    int lb = 0;
-    while (lb < 11 && ((long long)64 << lb) < M) ++lb;      // mean bucket ~64 until B = 2048
-    p.log2_buckets = lb;
-    const int B = 1 << lb;
-    const double mean = (double)M / (double)B;
-    // the slab buffer reuses the space of the per-warp histograms (never less than 64 KB of it)
-    const size_t hist = (size_t)PH_WARPS * (size_t)B * 4;
-    static const size_t slab_kb = getenv("PZ_PHILOX_SLAB_KB") ? (size_t)atoi(getenv("PZ_PHILOX_SLAB_KB")) : 72;
-    const size_t budget = hist > slab_kb * 1024 ? hist : slab_kb * 1024;
-    // as many buckets per slab as threads, fewer when the buckets are large: S mean + 8 sigma + slack
-    int S = B < PH_THREADS ? B : PH_THREADS;
-    auto need = [&](int k) { return (size_t)((double)k * mean + 8.0 * sqrt((double)k * mean) + 64.0); };
-    while (S > 1 && need(S) * 4 > budget) S >>= 1;
-    p.slab_buckets = S;
-    size_t cap = need(S);
-    if (cap * 4 < budget) cap = budget / 4;                 // use what is there anyway
-    if (cap * 4 > (size_t)160 * 1024) cap = (size_t)160 * 1024 / 4;     // (huge buckets take the global path)
-    p.slab_cap = (int)cap;
-    const size_t slab = cap * 4;
-    p.smem_bytes = (hist > slab ? hist : slab) + ((size_t)B + 1) * 4 + 64;
-    return p;
-}
-
-__global__ void __launch_bounds__(PH_THREADS) perm_philox_kernel(int32_t M, int32_t R,
-                                                                  const uint32_t *seeds, int32_t *perms,
-                                                                  int log2b, int slab_buckets, int slab_cap)
-{
-    extern __shared__ __align__(16) uint32_t sm[];
-    const int B = 1 << log2b;
-    const uint32_t bmask = (uint32_t)B - 1u;
-    uint32_t *start = sm;                       // [B + 1]
-    uint32_t *hist = sm + B + 1;                // [PH_WARPS][B] then per-warp bases
-    uint32_t *slab = sm + B + 1;                // [slab_cap]   (after the scatter)
-    __shared__ uint32_t scan_tot[PH_WARPS];
-
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    // contiguous element range of this warp (multiple of 128: one Philox call
-    // per lane covers four consecutive bonds)
-    const int per_warp = (((M + PH_WARPS - 1) / PH_WARPS) + 127) & ~127;
-    const int w_lo = min(M, warp * per_warp), w_hi = min(M, w_lo + per_warp);
-
-    for (int run = blockIdx.x; run < R; run += gridDim.x) {
-        const uint32_t seed = seeds[run];
-        int32_t *out = perms + (size_t)run * M;
-
-        // ---- A: per-warp histograms of the bucket draws ----------------------
-        for (int i = t; i < PH_WARPS * B; i += PH_THREADS) hist[i] = 0;
-        __syncthreads();
-        for (int i0 = w_lo + 4 * lane; i0 < w_hi; i0 += 128) {
-            uint32_t o[4];
-            philox_buckets4(seed, (uint32_t)i0 >> 2, o);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (i0 + q < w_hi) atomicAdd(&hist[warp * B + (o[q] & bmask)], 1u);
-        }
-        __syncthreads();
-
-        // ---- A': bucket starts (exclusive scan) and per-warp bases -----------
-        {
-            // thread t owns buckets [t*per, (t+1)*per)
-            const int per = (B + PH_THREADS - 1) / PH_THREADS;
-            const int b_lo = min(B, t * per), b_hi = min(B, b_lo + per);
-            uint32_t mine = 0;
-            for (int b = b_lo; b < b_hi; ++b)
-                for (int w = 0; w < PH_WARPS; ++w) mine += hist[w * B + b];
-            uint32_t incl = mine;
-            for (int k = 1; k < 32; k <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, k);
-                if (lane >= k) incl += o;
-            }
-            if (lane == 31) scan_tot[warp] = incl;
-            __syncthreads();
-            uint32_t pre = incl - mine;
-            for (int w = 0; w < warp; ++w) pre += scan_tot[w];
-            for (int b = b_lo; b < b_hi; ++b) {
-                start[b] = pre;
-                uint32_t run_base = pre;
-                for (int w = 0; w < PH_WARPS; ++w) {
-                    const uint32_t h = hist[w * B + b];
-                    hist[w * B + b] = run_base;
-                    run_base += h;
-                }
-                pre = run_base;
-            }
-            if (t == PH_THREADS - 1) start[B] = (uint32_t)M;
-        }
-        __syncthreads();
-
-        // ---- B: scatter.  Positions come from the per-warp bucket bases; two bonds
-        // of one warp instruction that share a bucket may land in either order, which
-        // phase C repairs by sorting the (almost sorted) bucket -- the order inside a
-        // bucket is ascending bond index whatever the timing.
-        for (int blk = w_lo; blk < w_hi; blk += 128) {
-            uint32_t o[4];
-            philox_buckets4(seed, (uint32_t)(blk + 4 * lane) >> 2, o);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int i = blk + 4 * lane + q;
-                if (i < w_hi) out[atomicAdd(&hist[warp * B + (o[q] & bmask)], 1u)] = i;
-            }
-        }
-        __syncthreads();
-
-        // ---- C: Fisher-Yates inside every bucket, in shared memory.  The buckets of a slab are
-        // contiguous in the output row: the CTA copies the slab in (coalesced), every thread
-        // restores the ascending bond order of its bucket and shuffles it, the CTA copies it back.
-        for (int b0 = 0; b0 < B; b0 += slab_buckets) {
-            const int b1 = min(B, b0 + slab_buckets);
-            const uint32_t lo = start[b0], n = start[b1] - lo;
-            const bool staged = n <= (uint32_t)slab_cap;      // CTA-uniform
-            if (staged) {
-                for (uint32_t k = t; k < n; k += PH_THREADS) slab[k] = (uint32_t)out[lo + k];
-                __syncthreads();
-            }
-            const int b = b0 + t;
-            if (b < b1) {
-                const uint32_t s0 = start[b], sz = start[b + 1] - s0;
-                if (sz > 1) {
-                    if (staged) {
-                        uint32_t *buf = slab + (s0 - lo);
-                        for (uint32_t k = 1; k < sz; ++k) {       // restore ascending bond order
-                            const uint32_t v = buf[k];
-                            uint32_t j = k;
-                            while (j > 0 && buf[j - 1] > v) { buf[j] = buf[j - 1]; --j; }
-                            buf[j] = v;
-                        }
-                        uint32_t o[4], grp = 0xffffffffu;
-                        for (uint32_t k = sz - 1; k >= 1; --k) {
-                            const uint32_t j = philox_bounded(seed, (uint32_t)b, k, o, grp);
-                            const uint32_t a = buf[k], c = buf[j];
-                            buf[k] = c; buf[j] = a;
-                        }
-                    } else {                      // a slab too large for shared memory: same sort + shuffle in place
-                        for (uint32_t k = 1; k < sz; ++k) {
-                            const int32_t v = out[s0 + k];
-                            uint32_t j = k;
-                            while (j > 0 && out[s0 + j - 1] > v) { out[s0 + j] = out[s0 + j - 1]; --j; }
-                            out[s0 + j] = v;
-                        }
-                        uint32_t o[4], grp = 0xffffffffu;
-                        for (uint32_t k = sz - 1; k >= 1; --k) {
-                            const uint32_t j = philox_bounded(seed, (uint32_t)b, k, o, grp);
-                            const int32_t a = out[s0 + k], c = out[s0 + j];
-                            out[s0 + k] = c; out[s0 + j] = a;
-                        }
-                    }
-                }
-            }
-            if (staged) {
-                __syncthreads();
-                for (uint32_t k = t; k < n; k += PH_THREADS) out[lo + k] = (int32_t)slab[k];
-            }
-            __syncthreads();
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------
-// The same permutation in two levels (M <= 131072, i.e. up to the L = 256 square lattice).
-// perm_philox_kernel scatters every bond to its bucket in global memory, one 4-byte store per
-// bond to 2048 places: with several hundred runs in flight the half-written sectors do not
-// survive in the L2, and the kernel is bound by that read-modify-write traffic to DRAM.  Here
-// the bucket number is split: its high bits name one of at most 16 SUPER-buckets, its low 7 bits
-// a bucket inside it.
-//   A  histogram of the bucket draws (bucket starts), per-warp counts of the super-buckets;
-//   B  every warp appends its bonds, in order, to its own segment of each super-bucket: 16
-//      sequential streams per warp, whose sectors fill within a few iterations and combine in
-//      the L2.  An entry carries its bucket: bond | low bits << 17;
-//   C  per super-bucket (about 8160 entries): per-warp counts of the 128 buckets, then a stable
-//      placement into shared memory in almost ascending order (warp after warp; only the entries
-//      of one warp instruction may swap), one thread per bucket restores the ascending bond order
-//      -- which makes the result independent of timing -- and shuffles
-//      it (Fisher-Yates, Philox draws), and the CTA writes the super-bucket out, coalesced.
-// DRAM traffic: about 16 bytes per bond, all of it sequential.
+// perm_philox: Rao-Sandelius in two levels.  Every bond draws one of B = 2^lb buckets (mean
+// bucket about 64 bonds, lb <= 17); the high bits of the bucket number name a SUPER-bucket of 128
+// buckets (about 8000 bonds), the low 7 bits a bucket inside it.
+//   A  per-warp counts of the super-buckets (one Philox call per four bonds), their starts;
+//   B  every warp appends its bonds, in order, to its own segment of each super-bucket:
+//      sequential streams, whose sectors fill within a few iterations and combine in the L2 (a
+//      direct scatter to thousands of buckets leaves half-written sectors that do not survive
+//      there with hundreds of runs in flight: that version was bound by read-modify-write
+//      traffic to DRAM).  An entry carries its bucket: bond | low bits << 24;
+//   C  per super-bucket: per-warp counts of its 128 buckets and their starts, placement into
+//      shared memory in almost ascending order (warp after warp; only the entries of one warp
+//      instruction may swap), one thread per bucket restores the ascending bond order -- which
+//      makes the result independent of timing -- and shuffles it (Fisher-Yates, Lemire-bounded
+//      Philox draws; the lanes of a warp walk the step index together so that all of them reach
+//      a new group of four draws in the same iteration), and the CTA writes the super-bucket
+//      out, coalesced.
+// DRAM traffic: about 16 bytes per bond, all of it sequential.  M <= 2^24 bonds.
 // ---------------------------------------------------------------------------
 static constexpr int PH2_SUB_LOG_MAX = 7;
+static constexpr int PH2_ID_BITS = 24;
 
 struct Philox2Plan {
     int log2_buckets, sub_log, supers;
@@ -318,15 +129,15 @@ static Philox2Plan plan_philox2(int32_t M)
 {
     Philox2Plan p{};
     int lb = 0;
-    while (lb < 11 && ((long long)64 << lb) < M) ++lb;
+    while (lb < 17 && ((long long)64 << lb) < M) ++lb;
     p.log2_buckets = lb;
     p.sub_log = lb < PH2_SUB_LOG_MAX ? lb : PH2_SUB_LOG_MAX;
     p.supers = 1 << (lb - p.sub_log);
     const double mean = (double)M / (double)p.supers;
     p.super_cap = p.supers == 1 ? std::max(M, 1) : (int)(mean + 10.0 * sqrt(mean) + 64.0);
-    const size_t B = (size_t)1 << lb;
-    p.smem_bytes = (B + 1) * 4 + (size_t)PH_WARPS * (p.supers + 1) * 4 +
-                   (size_t)PH_WARPS * ((size_t)1 << p.sub_log) * 4 + (size_t)p.super_cap * 4 + 64;
+    const size_t nsub = (size_t)1 << p.sub_log;
+    p.smem_bytes = ((size_t)PH_WARPS + 1) * (p.supers + 1) * 4 + ((size_t)PH_WARPS + 1) * (nsub + 1) * 4 +
+                   (size_t)p.super_cap * 4 + 64;
     return p;
 }
 
@@ -338,62 +149,66 @@ __global__ void __launch_bounds__(PH_THREADS) perm_philox2_kernel(int32_t M, int
     const int B = 1 << log2b;
     const uint32_t bmask = (uint32_t)B - 1u;
     const int NSUB = 1 << sub_log, SB = B >> sub_log;
-    uint32_t *start = sm;                               // [B + 1]  counts, then bucket starts
-    uint32_t *wsuper = start + B + 1;                   // [PH_WARPS][SB]  counts, then the warps' append positions
-    uint32_t *wsub = wsuper + PH_WARPS * (SB + 1);      // [PH_WARPS][NSUB]
-    uint32_t *buf = wsub + PH_WARPS * NSUB;             // [super_cap]
+    uint32_t *sstart = sm;                              // [SB + 1]  super-bucket starts
+    uint32_t *wsuper = sstart + SB + 1;                 // [PH_WARPS][SB + 1]  counts, then the warps' append positions
+    uint32_t *bstart = wsuper + PH_WARPS * (SB + 1);    // [NSUB + 1]  bucket starts inside the super-bucket
+    uint32_t *wsub = bstart + NSUB + 1;                 // [PH_WARPS][NSUB + 1]
+    uint32_t *buf = wsub + PH_WARPS * (NSUB + 1);       // [super_cap]
     __shared__ uint32_t scan_tot[PH_WARPS];
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int per_warp = (((M + PH_WARPS - 1) / PH_WARPS) + 127) & ~127;
     const int w_lo = min(M, warp * per_warp), w_hi = min(M, w_lo + per_warp);
 
+    // exclusive scan over `cnt` values spread one run of `per` per thread; returns this thread's
+    // prefix (callers write the results)
+    auto block_excl = [&](uint32_t mine) -> uint32_t {
+        uint32_t incl = mine;
+        for (int k = 1; k < 32; k <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, k);
+            if (lane >= k) incl += o;
+        }
+        __syncthreads();                        // (scan_tot of the previous use has been read)
+        if (lane == 31) scan_tot[warp] = incl;
+        __syncthreads();
+        uint32_t pre = incl - mine;
+        for (int w = 0; w < warp; ++w) pre += scan_tot[w];
+        return pre;
+    };
+
     for (int run = blockIdx.x; run < R; run += gridDim.x) {
         const uint32_t seed = seeds[run];
         int32_t *out = perms + (size_t)run * M;
 
-        // ---- A: bucket counts, per-warp super-bucket counts -------------------------------
-        for (int i = t; i < B + 1 + PH_WARPS * (SB + 1); i += PH_THREADS) sm[i] = 0;
+        // ---- A: per-warp super-bucket counts -----------------------------------------------
+        for (int i = t; i < (PH_WARPS + 1) * (SB + 1); i += PH_THREADS) sm[i] = 0;
         __syncthreads();
         for (int i0 = w_lo + 4 * lane; i0 < w_hi; i0 += 128) {
             uint32_t o[4];
             philox_buckets4(seed, (uint32_t)i0 >> 2, o);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-                if (i0 + q < w_hi) {
-                    const uint32_t b = o[q] & bmask;
-                    atomicAdd(&start[b], 1u);
-                    atomicAdd(&wsuper[warp * (SB + 1) + (b >> sub_log)], 1u);
-                }
+                if (i0 + q < w_hi) atomicAdd(&wsuper[warp * (SB + 1) + ((o[q] & bmask) >> sub_log)], 1u);
         }
         __syncthreads();
         {
-            // exclusive scan of the bucket counts: thread t owns buckets [t*per, (t+1)*per)
-            const int per = (B + PH_THREADS - 1) / PH_THREADS;
-            const int b_lo = min(B, t * per), b_hi = min(B, b_lo + per);
+            // super-bucket starts: thread t owns super-buckets [t*per, (t+1)*per); warp w appends to a
+            // super-bucket behind the warps before it
+            const int per = (SB + PH_THREADS - 1) / PH_THREADS;
+            const int s_lo = min(SB, t * per), s_hi = min(SB, s_lo + per);
             uint32_t mine = 0;
-            for (int b = b_lo; b < b_hi; ++b) mine += start[b];
-            uint32_t incl = mine;
-            for (int k = 1; k < 32; k <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, k);
-                if (lane >= k) incl += o;
+            for (int sp = s_lo; sp < s_hi; ++sp)
+                for (int w = 0; w < PH_WARPS; ++w) mine += wsuper[w * (SB + 1) + sp];
+            uint32_t pos = block_excl(mine);
+            for (int sp = s_lo; sp < s_hi; ++sp) {
+                sstart[sp] = pos;
+                for (int w = 0; w < PH_WARPS; ++w) {
+                    const uint32_t c = wsuper[w * (SB + 1) + sp];
+                    wsuper[w * (SB + 1) + sp] = pos;
+                    pos += c;
+                }
             }
-            if (lane == 31) scan_tot[warp] = incl;
-            __syncthreads();
-            uint32_t pre = incl - mine;
-            for (int w = 0; w < warp; ++w) pre += scan_tot[w];
-            for (int b = b_lo; b < b_hi; ++b) { const uint32_t c = start[b]; start[b] = pre; pre += c; }
-            if (t == PH_THREADS - 1) start[B] = (uint32_t)M;
-        }
-        __syncthreads();
-        if (t < SB) {
-            // warp w appends to super-bucket t behind the warps before it
-            uint32_t pos = start[t << sub_log];
-            for (int w = 0; w < PH_WARPS; ++w) {
-                const uint32_t c = wsuper[w * (SB + 1) + t];
-                wsuper[w * (SB + 1) + t] = pos;
-                pos += c;
-            }
+            if (t == PH_THREADS - 1) sstart[SB] = (uint32_t)M;
         }
         __syncthreads();
 
@@ -404,35 +219,42 @@ __global__ void __launch_bounds__(PH_THREADS) perm_philox2_kernel(int32_t M, int
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int i = blk + 4 * lane + q;
-                const uint32_t b = o[q] & bmask, sp = b >> sub_log;
+                const uint32_t b = o[q] & bmask;
                 // (two bonds of one warp instruction that share a super-bucket may land in either
                 // order: phase C sorts every bucket, so the result does not depend on it)
                 if (i < w_hi)
-                    out[atomicAdd(&wsuper[warp * (SB + 1) + sp], 1u)] =
-                        (int32_t)((uint32_t)i | ((b & (NSUB - 1)) << 17));
+                    out[atomicAdd(&wsuper[warp * (SB + 1) + (b >> sub_log)], 1u)] =
+                        (int32_t)((uint32_t)i | ((b & (NSUB - 1)) << PH2_ID_BITS));
             }
         }
         __syncthreads();
 
         // ---- C: super-bucket by super-bucket ----------------------------------------------------
         for (int sp = 0; sp < SB; ++sp) {
-            const uint32_t lo = start[sp << sub_log], n = start[(sp + 1) << sub_log] - lo;
+            const uint32_t lo = sstart[sp], n = sstart[sp + 1] - lo;
             if (n > (uint32_t)super_cap) __trap();       // (ten standard deviations above the mean)
             // per-warp counts of the buckets: warp w owns the entries [w*ch, (w+1)*ch) of the super-bucket
             const uint32_t ch = ((n + PH_WARPS - 1) / PH_WARPS + 31u) & ~31u;
             const uint32_t c_lo = min(n, warp * ch), c_hi = min(n, c_lo + ch);
-            for (int i = t; i < PH_WARPS * NSUB; i += PH_THREADS) wsub[i] = 0;
+            for (int i = t; i < PH_WARPS * (NSUB + 1); i += PH_THREADS) wsub[i] = 0;
             __syncthreads();
             for (uint32_t k = c_lo + lane; k < c_hi; k += 32)
-                atomicAdd(&wsub[warp * NSUB + ((uint32_t)out[lo + k] >> 17)], 1u);
+                atomicAdd(&wsub[warp * (NSUB + 1) + ((uint32_t)out[lo + k] >> PH2_ID_BITS)], 1u);
             __syncthreads();
-            if (t < NSUB) {
-                uint32_t pos = start[(sp << sub_log) + t] - lo;
-                for (int w = 0; w < PH_WARPS; ++w) {
-                    const uint32_t c = wsub[w * NSUB + t];
-                    wsub[w * NSUB + t] = pos;
-                    pos += c;
+            {
+                uint32_t mine = 0;
+                if (t < NSUB)
+                    for (int w = 0; w < PH_WARPS; ++w) mine += wsub[w * (NSUB + 1) + t];
+                uint32_t pos = block_excl(mine);
+                if (t < NSUB) {
+                    bstart[t] = pos;
+                    for (int w = 0; w < PH_WARPS; ++w) {
+                        const uint32_t c = wsub[w * (NSUB + 1) + t];
+                        wsub[w * (NSUB + 1) + t] = pos;
+                        pos += c;
+                    }
                 }
+                if (t == 0) bstart[NSUB] = n;
             }
             __syncthreads();
             // placement: warps by their bases, the entries of one warp instruction in any order
@@ -442,25 +264,19 @@ __global__ void __launch_bounds__(PH_THREADS) perm_philox2_kernel(int32_t M, int
                 const bool ok = k < c_hi;
                 const uint32_t v = v_next;
                 if (k + 32 < c_hi) v_next = (uint32_t)out[lo + k + 32];     // the next step's load is in flight
-                if (ok) buf[atomicAdd(&wsub[warp * NSUB + (v >> 17)], 1u)] = v & 0x1ffffu;
+                if (ok) buf[atomicAdd(&wsub[warp * (NSUB + 1) + (v >> PH2_ID_BITS)], 1u)] = v & ((1u << PH2_ID_BITS) - 1u);
             }
             __syncthreads();
             if (t < NSUB) {
                 const int b = (sp << sub_log) + t;
-                const uint32_t s0 = start[b] - lo, sz = start[b + 1] - start[b];
-                if (sz > 1) {
-                    uint32_t *x = buf + s0;
-                    for (uint32_t k = 1; k < sz; ++k) {       // restore ascending bond order
-                        const uint32_t v = x[k];
-                        uint32_t j = k;
-                        while (j > 0 && x[j - 1] > v) { x[j] = x[j - 1]; --j; }
-                        x[j] = v;
-                    }
-                }
-                // the lanes of a warp walk k together from the largest bucket down: then all of them
-                // reach a new group of four draws (one Philox call) in the same iteration -- with a
-                // private k per lane some lane needs a call in nearly every iteration
+                const uint32_t s0 = bstart[t], sz = bstart[t + 1] - s0;
                 uint32_t *x = buf + s0;
+                for (uint32_t k = 1; k < sz; ++k) {       // restore ascending bond order
+                    const uint32_t v = x[k];
+                    uint32_t j = k;
+                    while (j > 0 && x[j - 1] > v) { x[j] = x[j - 1]; --j; }
+                    x[j] = v;
+                }
                 const uint32_t kmax = __reduce_max_sync(__activemask(), sz);
                 uint32_t o[4] = {0u, 0u, 0u, 0u};
                 for (uint32_t k = kmax - 1; k >= 1 && kmax > 1; --k) {
@@ -486,28 +302,17 @@ cudaError_t launch_perm_philox(int32_t M, int32_t R, const uint32_t *seeds, int3
 {
     *launches = 0;
     if (R <= 0 || M <= 0) return cudaSuccess;
-    static const bool two_level = !(getenv("PZ_PHILOX_TWO_LEVEL") && atoi(getenv("PZ_PHILOX_TWO_LEVEL")) == 0);
-    if (two_level && M <= 131072) {
-        const Philox2Plan p = plan_philox2(M);
-        cudaError_t e = cudaFuncSetAttribute(perm_philox2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)p.smem_bytes);
-        if (e != cudaSuccess) return e;
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const int grid = std::min(R, sms * 8);
-        perm_philox2_kernel<<<grid, PH_THREADS, p.smem_bytes, s>>>(M, R, seeds, perms, p.log2_buckets, p.sub_log,
-                                                                   p.super_cap);
-        *launches = 1;
-        return cudaGetLastError();
-    }
-    const PhiloxPlan p = plan_philox(M);
-    cudaError_t e = cudaFuncSetAttribute(perm_philox_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if ((long long)M > (1ll << PH2_ID_BITS)) return cudaErrorInvalidValue;      // (documented limit of this mode)
+    const Philox2Plan p = plan_philox2(M);
+    cudaError_t e = cudaFuncSetAttribute(perm_philox2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)p.smem_bytes);
     if (e != cudaSuccess) return e;
-    perm_philox_kernel<<<R, PH_THREADS, p.smem_bytes, s>>>(M, R, seeds, perms, p.log2_buckets,
-                                                           p.slab_buckets, p.slab_cap);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = std::min(R, sms * 8);
+    perm_philox2_kernel<<<grid, PH_THREADS, p.smem_bytes, s>>>(M, R, seeds, perms, p.log2_buckets, p.sub_log,
+                                                               p.super_cap);
     *launches = 1;
     return cudaGetLastError();
 }

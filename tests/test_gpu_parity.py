@@ -122,7 +122,8 @@ def test_philox_bond_orders_match_restatement():
     from pypercolate_b200 import lowering
     from oracle import oracle
     n = _native()
-    for L in (3, 8, 32, 128, 256):
+    # (up to L = 256 the bucket count stops at 2048; beyond, it grows with the number of bonds)
+    for L in (2, 3, 8, 32, 100, 128, 181, 256, 300, 512, 1024):
         g = lowering.lowered_spanning_2d_grid(L)
         ctx = ctx_for(g)
         seeds = np.array([0, 1, 42, 2 ** 32 - 1, 99], dtype=np.uint32)
