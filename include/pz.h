@@ -39,7 +39,8 @@ enum pz_perm_mode {
     PZ_PERM_DEVICE = 1,    /* same layout, pointer is device memory                      */
     PZ_PERM_MT19937 = 2,   /* uint32 seeds[R]; numpy RandomState(seed).permutation(M)
                               reproduced on the device bit for bit                      */
-    PZ_PERM_PHILOX = 3,    /* uint32 seeds[R]; Philox4x32-10 bucketed Fisher-Yates       */
+    PZ_PERM_PHILOX = 3,    /* uint32 seeds[R]; counter-based Philox4x32-10 Fisher-Yates in
+                              shared memory (bucketed, exact uniform shuffle; M <= 2^24)  */
     PZ_PERM_FEISTEL = 4,   /* uint32 seeds[R]; Philox-keyed 20-round Feistel bijection of
                               [0, M) with cycle walking: order[n] = pi_seed(n), no
                               scratch and no shared memory                              */

@@ -68,7 +68,10 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1,
 }
 
 static constexpr uint32_t PHILOX_KEY1 = 0x50455243u;   // 'PERC'
-static constexpr int PH_THREADS = 256;
+#ifndef PZ_PH_THREADS
+#define PZ_PH_THREADS 256
+#endif
+static constexpr int PH_THREADS = PZ_PH_THREADS;
 static constexpr int PH_WARPS = PH_THREADS / 32;
 
 // the four bucket words of bonds 4g .. 4g+3
