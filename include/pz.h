@@ -46,7 +46,7 @@ enum pz_perm_mode {
                               scratch and no shared memory                              */
     PZ_PERM_PHILOX_FY = 5  /* uint32 seeds[R]; textbook Fisher-Yates (i = M-1..1, swap with
                               j in [0, i]) with unbiased Lemire draws from Philox4x32-10
-                              counters: one thread per run, no shared memory; like
+                              counters: one warp per run, no shared memory; like
                               PZ_PERM_MT19937 it is generated underneath the sweep of the
                               previous batch of runs                                    */
 };
