@@ -15,7 +15,7 @@ from pypercolate_b200 import (  # noqa: F401  (the names percolate/__init__.py:8
     canonical_averages, spanning_1d_chain, spanning_2d_grid, statistics,
 )
 
-for _name in ("hpc", "percolate", "lowering", "study", "multi"):
+for _name in ("hpc", "percolate", "lowering", "study", "multi", "site"):
     _mod = __import__("pypercolate_b200." + _name, fromlist=["_"])
     _sys.modules[__name__ + "." + _name] = _mod
     globals()[_name] = _mod

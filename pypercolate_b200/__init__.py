@@ -7,7 +7,7 @@ hand-written sm_100a CUDA kernels behind the C-ABI of ``include/pz.h``; there
 is no CPU fallback.
 """
 
-from . import hpc, lowering, percolate, study  # noqa: F401
+from . import hpc, lowering, percolate, site, study  # noqa: F401
 from .percolate import (  # noqa: F401
     sample_states,
     single_run_arrays,
