@@ -670,10 +670,20 @@ int pz_run_fused(pz_ctx *c, int32_t R, int perm_mode, const void *perm_src, int 
     // be visible to the side streams
     PZ_CUDA(cudaStreamSynchronize(c->stream));
     const int P = c->num_p;
+    const SweepPlan p0 = plan_sweep(c->N, R, c->sms, c->smem_optin, c->force_kind, c->team,
+                                    c->claim_cap, c->cta_warps);
+    // Streams (measured, profiles/rng_r2.txt).  2: the bond orders of chunk k+1 on a second stream
+    // under the sweep of chunk k.  The bucketed Philox shuffle needs shared memory: next to a sweep
+    // that fills the SMs' shared memory its CTAs follow the sweep's as those retire and run beside
+    // the statistics kernels (-1 %); next to a global-memory sweep they would share the SMs with it
+    // and halve its pace (L = 1024: 420 instead of 284 ms), so there it stays on the main stream.
+    // 1: in addition the statistics kernels of chunk k on a third stream under the sweep of chunk
+    // k+1: +4.5 % at 12500 runs, +2.4 % at 25000, +0.5 % at 50000, -3 % at 100000 (the contraction
+    // kernel crawls next to a long sweep), hence for calls of moderate size only.
     const int pipeline = (base_mode == PZ_PERM_HOST || base_mode == PZ_PERM_DEVICE) ? 0
                          : c->pipeline >= 0 ? c->pipeline
-                         : 2;     // (the bucketed Philox shuffle needs shared memory: its CTAs follow the
-                                  //  sweep's as those retire and run next to the statistics kernels)
+                         : (base_mode == PZ_PERM_PHILOX && p0.kind == STORE_G32) ? 0
+                         : (p0.kind != STORE_G32 && R <= 60000) ? 1 : 2;
     // three slots rotate even on one stream: the host then runs up to two chunks ahead of the
     // device instead of waiting for every chunk's statistics before it launches the next sweep
     const int nslot = pz_ctx::PZ_SLOTS;
@@ -682,11 +692,7 @@ int pz_run_fused(pz_ctx *c, int32_t R, int perm_mode, const void *perm_src, int 
                            ((size_t)c->M / c->ckpt_every + 1) * 32;  // + checkpoints
     // the global-memory store keeps one parent array per resident sweep CTA next to the slots
     size_t budget = c->chunk_bytes;
-    {
-        const SweepPlan p0 = plan_sweep(c->N, R, c->sms, c->smem_optin, c->force_kind, c->team,
-                                        c->claim_cap, c->cta_warps);
-        budget = p0.gscratch_bytes < budget / 2 ? budget - p0.gscratch_bytes : budget / 2;
-    }
+    budget = p0.gscratch_bytes < budget / 2 ? budget - p0.gscratch_bytes : budget / 2;
     size_t chunk = std::max<size_t>(1, (budget / pz_ctx::PZ_SLOTS) / per_run);
     // Chunk sizes: whole waves (one run per sweep CTA, grid = a multiple of the SM count), as few
     // equal chunks as the scratch allows.  With the bond orders on their own stream: at least three
