@@ -112,6 +112,7 @@ struct pz_ctx {
     DevBuf<int32_t> band_lo, band_hi, tband_lo, tband_hi, porder_dev, canon_flags;
     DevBuf<double> sf;                    // survival functions [num_p][M+1]
     DevBuf<int32_t> perm_stage;           // warp-per-run shuffles: one L2-resident staging row per warp
+    int gen_sms = 0;                      // SMs a warp-per-run shuffle keeps to itself next to a sweep (PZ_GEN_SMS; 0: shares them)
     DevBuf<uint32_t> validate_bits;       // caller-supplied orders: one bit per (run, bond) + flag word
     int *validate_host = nullptr;         // pinned copy of the flag word
     uint32_t epoch_start = 0x003fffffu;   // first claim epoch of a run (PZ_EPOCH_START: tests)
@@ -200,18 +201,18 @@ cudaError_t launch_canon_reduce(int32_t R, int32_t cols, const double *runs, dou
 cudaError_t launch_perm_philox(int32_t M, int32_t R, const uint32_t *seeds, int32_t *perms,
                                cudaStream_t s, int *launches);
 cudaError_t launch_perm_mt19937(int32_t M, int32_t R, const uint32_t *seeds, int32_t *perms,
-                                int32_t *stage, cudaStream_t s, int *launches);
-size_t perm_stage_ints(int sms, int32_t M);
+                                int32_t *stage, int excl_sms, cudaStream_t s, int *launches);
+size_t perm_stage_ints(int sms, int32_t M, int excl_sms);
 cudaError_t launch_perm_feistel(int32_t M, int32_t R, const uint32_t *seeds, int32_t *perms,
                                 cudaStream_t s, int *launches);
 cudaError_t launch_perm_philox_fy(int32_t M, int32_t R, const uint32_t *seeds, int32_t *perms,
-                                  int32_t *stage, cudaStream_t s, int *launches);
+                                  int32_t *stage, int excl_sms, cudaStream_t s, int *launches);
 cudaError_t launch_validate_orders(int32_t M, int32_t R, const int32_t *perms, uint32_t *bitmap,
                                    int *flag, cudaStream_t s);
 }
 
 static cudaError_t launch_perm_mode(pz_ctx *c, int perm_mode, int32_t M, int32_t R, const uint32_t *seeds,
-                                    int32_t *perms, cudaStream_t s, int *l)
+                                    int32_t *perms, cudaStream_t s, int *l, int excl_sms = 0)
 {
     switch (perm_mode) {
     case PZ_PERM_PHILOX: return launch_perm_philox(M, R, seeds, perms, s, l);
@@ -220,10 +221,11 @@ static cudaError_t launch_perm_mode(pz_ctx *c, int perm_mode, int32_t M, int32_t
     }
     // warp-per-run shuffles: one staging row per warp of the launch (allocated once per graph size;
     // launches of one context are ordered on a stream, so they never share it concurrently)
-    cudaError_t e = c->perm_stage.ensure(perm_stage_ints(c->sms, M));
+    cudaError_t e = c->perm_stage.ensure(perm_stage_ints(c->sms, M, c->gen_sms));
     if (e != cudaSuccess) return e;
-    if (perm_mode == PZ_PERM_PHILOX_FY) return launch_perm_philox_fy(M, R, seeds, perms, c->perm_stage.p, s, l);
-    return launch_perm_mt19937(M, R, seeds, perms, c->perm_stage.p, s, l);
+    if (perm_mode == PZ_PERM_PHILOX_FY)
+        return launch_perm_philox_fy(M, R, seeds, perms, c->perm_stage.p, excl_sms, s, l);
+    return launch_perm_mt19937(M, R, seeds, perms, c->perm_stage.p, excl_sms, s, l);
 }
 
 extern "C" {
@@ -254,6 +256,7 @@ int pz_create(int device, pz_ctx **out)
         PZ_CUDA(cudaEventCreateWithFlags(&sl.stats_done, cudaEventDisableTiming));
     }
     if (const char *e = getenv("PZ_PIPELINE")) c->pipeline = atoi(e);
+    if (const char *e = getenv("PZ_GEN_SMS")) c->gen_sms = std::max(0, std::min(atoi(e), 100));
     if (const char *e = getenv("PZ_FORCE_STORE")) c->force_kind = atoi(e);
     if (const char *e = getenv("PZ_SWEEP_TEAM")) c->team = atoi(e);
     if (const char *e = getenv("PZ_CLAIM_LOG2")) c->claim_cap = atoi(e);
@@ -426,7 +429,8 @@ struct Chunk {
 // bond orders of the chunk on `sp` (slot buffers), then the sweep on the
 // context's main stream; `sl.sweep_done` is recorded behind the sweep
 static int sweep_chunk(pz_ctx *c, pz_ctx::Slot &sl, cudaStream_t sp, int32_t R, int perm_mode_in,
-                       const void *perm_src, size_t run0, Chunk *out)
+                       const void *perm_src, size_t run0, Chunk *out, int gen_excl_sms = 0,
+                       int sweep_grid_cap = 0)
 {
     const int32_t M = c->M;
     const bool seeds_on_device = (perm_mode_in & PZ_SEEDS_ON_DEVICE) != 0;
@@ -452,7 +456,7 @@ static int sweep_chunk(pz_ctx *c, pz_ctx::Slot &sl, cudaStream_t sp, int32_t R, 
             }
             int l = 0;
             PhaseTimer t(c, PZ_PHASE_PERM, sp);
-            PZ_CUDA(launch_perm_mode(c, perm_mode, M, R, seeds_dev, sl.perms.p, sp, &l));
+            PZ_CUDA(launch_perm_mode(c, perm_mode, M, R, seeds_dev, sl.perms.p, sp, &l, gen_excl_sms));
             c->launches += l;
         }
     }
@@ -471,6 +475,7 @@ static int sweep_chunk(pz_ctx *c, pz_ctx::Slot &sl, cudaStream_t sp, int32_t R, 
             return fail(PZ_ERR_ARG, "bond order is not a permutation (repeated entry)");
     }
     SweepPlan plan = plan_sweep(c->N, R, c->sms, c->smem_optin, c->force_kind, c->team, c->claim_cap, c->cta_warps);
+    if (sweep_grid_cap > 0 && plan.grid > sweep_grid_cap) plan.grid = sweep_grid_cap;   // (runs are grid-stride)
     if (plan.kind != STORE_G32 && c->N > 65536)
         return fail(PZ_ERR_ARG, "forced shared-memory store needs N <= 65536");
     const bool rec64 = plan.kind == STORE_G32;
@@ -687,6 +692,8 @@ int pz_run_fused(pz_ctx *c, int32_t R, int perm_mode, const void *perm_src, int 
     // three slots rotate even on one stream: the host then runs up to two chunks ahead of the
     // device instead of waiting for every chunk's statistics before it launches the next sweep
     const int nslot = pz_ctx::PZ_SLOTS;
+    const bool split_sms = (base_mode == PZ_PERM_MT19937 || base_mode == PZ_PERM_PHILOX_FY) && c->gen_sms > 0 &&
+                           p0.kind != STORE_G32 && p0.grid >= c->sms && p0.smem_bytes > (size_t)114 * 1024;
     const bool hide = pipeline != 0;          // bond orders are generated underneath the previous sweep
     const size_t per_run = (size_t)std::max(c->M, 1) * 12 + 4096 +   // orders + widest records
                            ((size_t)c->M / c->ckpt_every + 1) * 32;  // + checkpoints
@@ -741,7 +748,14 @@ int pz_run_fused(pz_ctx *c, int32_t R, int perm_mode, const void *perm_src, int 
             PZ_CUDA(cudaEventSynchronize(sl.stats_done));
         }
         Chunk ch;
-        rc = sweep_chunk(c, sl, sp, n, perm_mode, perm_src, r0, &ch);
+        // Warp-per-run shuffles next to a one-CTA-per-SM sweep: sharing the SMs costs the sweep 40 %
+        // (the shuffle's uncoalesced accesses share the load/store pipe with the sweep's shared-
+        // memory chains), so the bond orders of chunk ci are generated on gen_sms SMs of their own
+        // while the sweep of chunk ci - 1 runs on the others (its grid is capped accordingly; the
+        // first chunk's orders have the whole GPU, the last sweep as well).
+        const bool part = split_sms && pipeline != 0;
+        rc = sweep_chunk(c, sl, sp, n, perm_mode, perm_src, r0, &ch, part && ci > 0 ? c->gen_sms : 0,
+                         part && ci + 1 < sizes.size() ? c->sms - c->gen_sms : 0);
         if (rc) return rc;
         PZ_CUDA(sl.ckpt.ensure((size_t)n * n_ckpt));
         if (ss != c->stream) PZ_CUDA(cudaStreamWaitEvent(ss, sl.sweep_done, 0));

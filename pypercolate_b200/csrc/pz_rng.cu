@@ -2,14 +2,13 @@
 //
 // The reference draws the bond order of a run on the host,
 // ``RandomState(seed).permutation(M)`` (percolate/hpc.py:195,206).  Two device
-// replacements:
+// replacements (and two more of this package's own, further down):
 //
 //  * perm_mt19937: NumPy's legacy stream reproduced bit for bit -- MT19937
 //    seeded by init_genrand(seed), then the legacy shuffle (for i = M-1..1:
-//    j = masked-rejection draw in [0, i]; swap).  One thread per run; the
-//    twister state lives in thread-local memory, the permutation in the run's
-//    row of the output (HBM-resident, latency hidden by running every run of
-//    the batch concurrently).
+//    j = masked-rejection draw in [0, i]; swap).  One WARP per run
+//    (perm_warp_kernel): the twister state lives in registers across the warp,
+//    32 shuffle steps are drawn and applied together.
 //
 //  * perm_philox: counter-based Philox4x32-10.  A uniform permutation is built
 //    in two exact steps (Rao-Sandelius): every bond draws one of B buckets
@@ -428,7 +427,8 @@ cudaError_t launch_perm_feistel(int32_t M, int32_t R, const uint32_t *seeds, int
 // sweep CTA that owns the rest of the SM, so the bond orders of the next batch of runs are
 // generated underneath the sweep of the current one.
 // ---------------------------------------------------------------------------
-static constexpr int WP_WARPS = 8;             // most warps a CTA of the kernel may have
+static constexpr int WP_WARPS = 8;             // warps per CTA of a shared launch
+static constexpr int WP_WARPS_EXCL = 32;       // ... of a launch that has SMs to itself
 static constexpr uint32_t FULL = 0xffffffffu;
 
 struct WarpRow {
@@ -595,7 +595,7 @@ __device__ __forceinline__ void wp_iota(int32_t *x, int32_t M, int lane)
     }
 
 template <bool MT>
-__global__ void __launch_bounds__(32 * WP_WARPS, 4) perm_warp_kernel(int32_t M, int32_t R, const uint32_t *seeds,
+__global__ void __launch_bounds__(32 * WP_WARPS_EXCL, 1) perm_warp_kernel(int32_t M, int32_t R, const uint32_t *seeds,
                                                                       int32_t *perms, int32_t *stage,
                                                                       size_t stage_stride)
 {
@@ -664,33 +664,43 @@ __global__ void __launch_bounds__(32 * WP_WARPS, 4) perm_warp_kernel(int32_t M, 
     }
 }
 
-// Shape of a launch: PZ_WP_CTAS CTAs per SM (default 2; next to a sweep CTA one of them is resident
-// at a time), PZ_WP_WARPS warps each (default 8); every warp owns one staging row.  Measured on one
-// B200 (profiles/rng_r2.txt): the shuffle saturates at about 1200 warps (2.2e10 bonds/s, bound by
-// the random sector traffic of the staging rows); large graphs take fewer warps so that the
-// staging rows stay below 2 GB.
-void perm_warp_shape(int sms, int32_t M, int *ctas, int *wpc, size_t *stride)
+// Shape of a launch.  Shared (excl_sms == 0): PZ_WP_CTAS CTAs per SM (default 2; next to a sweep CTA
+// one of them is resident at a time), PZ_WP_WARPS warps each (default 8).  Exclusive (excl_sms > 0):
+// one CTA of 32 warps on each of excl_sms SMs, which it keeps to itself by asking for most of the
+// SM's shared memory -- the sweep of the previous chunk runs on the other SMs.  Every warp owns one
+// staging row.  Measured on one B200 (profiles/rng_r2.txt): the shuffle saturates at about 1200
+// warps (2.2e10 bonds/s, bound by the random sector traffic of the staging rows); large graphs take
+// fewer warps so that the staging rows stay below 2 GB.
+static constexpr size_t WP_EXCL_SMEM = 160 * 1024;
+
+void perm_warp_shape(int sms, int32_t M, int excl_sms, int *ctas, int *wpc, size_t *stride)
 {
     static const int per_sm = getenv("PZ_WP_CTAS") ? std::max(1, atoi(getenv("PZ_WP_CTAS"))) : 2;
     static const int w = getenv("PZ_WP_WARPS") ? std::min(WP_WARPS, std::max(1, atoi(getenv("PZ_WP_WARPS")))) : 8;
-    *ctas = sms * per_sm;
-    *wpc = w;
+    *ctas = excl_sms > 0 ? excl_sms : sms * per_sm;
+    *wpc = excl_sms > 0 ? WP_WARPS_EXCL : w;
     *stride = ((size_t)std::max(M, 1) + 31) / 32 * 32;
     const size_t budget = (size_t)2 << 30;
     while (*wpc > 1 && (size_t)*ctas * *wpc * *stride * 4 > budget) *wpc >>= 1;
-    while (*ctas > sms && (size_t)*ctas * *wpc * *stride * 4 > budget) *ctas -= sms;
-    while (*ctas > 1 && (size_t)*ctas * *wpc * *stride * 4 > budget) *ctas >>= 1;
+    while (excl_sms == 0 && *ctas > sms && (size_t)*ctas * *wpc * *stride * 4 > budget) *ctas -= sms;
+    while (excl_sms == 0 && *ctas > 1 && (size_t)*ctas * *wpc * *stride * 4 > budget) *ctas >>= 1;
 }
 
-size_t perm_stage_ints(int sms, int32_t M)
+size_t perm_stage_ints(int sms, int32_t M, int excl_sms)
 {
     int ctas, wpc; size_t stride;
-    perm_warp_shape(sms, M, &ctas, &wpc, &stride);
-    return (size_t)ctas * wpc * stride;
+    perm_warp_shape(sms, M, 0, &ctas, &wpc, &stride);
+    size_t need = (size_t)ctas * wpc * stride;
+    if (excl_sms > 0) {
+        perm_warp_shape(sms, M, excl_sms, &ctas, &wpc, &stride);
+        need = std::max(need, (size_t)ctas * wpc * stride);
+    }
+    return need;
 }
 
 static cudaError_t launch_perm_serial(int mode_mt, int32_t M, int32_t R, const uint32_t *seeds,
-                                      int32_t *perms, int32_t *stage, cudaStream_t s, int *launches)
+                                      int32_t *perms, int32_t *stage, int excl_sms, cudaStream_t s,
+                                      int *launches)
 {
     *launches = 0;
     if (R <= 0 || M <= 0) return cudaSuccess;
@@ -698,25 +708,30 @@ static cudaError_t launch_perm_serial(int mode_mt, int32_t M, int32_t R, const u
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int ctas, wpc; size_t stride;
-    perm_warp_shape(sms, M, &ctas, &wpc, &stride);
+    perm_warp_shape(sms, M, excl_sms, &ctas, &wpc, &stride);
     const int need = (R + wpc - 1) / wpc;
     if (ctas > need) ctas = need;
-    if (mode_mt) perm_warp_kernel<true><<<ctas, 32 * wpc, 0, s>>>(M, R, seeds, perms, stage, stride);
-    else perm_warp_kernel<false><<<ctas, 32 * wpc, 0, s>>>(M, R, seeds, perms, stage, stride);
+    const size_t smem = excl_sms > 0 ? WP_EXCL_SMEM : 0;
+    auto kern = mode_mt ? perm_warp_kernel<true> : perm_warp_kernel<false>;
+    if (smem) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    kern<<<ctas, 32 * wpc, smem, s>>>(M, R, seeds, perms, stage, stride);
     *launches = 1;
     return cudaGetLastError();
 }
 
 cudaError_t launch_perm_mt19937(int32_t M, int32_t R, const uint32_t *seeds, int32_t *perms,
-                                int32_t *stage, cudaStream_t s, int *launches)
+                                int32_t *stage, int excl_sms, cudaStream_t s, int *launches)
 {
-    return launch_perm_serial(1, M, R, seeds, perms, stage, s, launches);
+    return launch_perm_serial(1, M, R, seeds, perms, stage, excl_sms, s, launches);
 }
 
 cudaError_t launch_perm_philox_fy(int32_t M, int32_t R, const uint32_t *seeds, int32_t *perms,
-                                  int32_t *stage, cudaStream_t s, int *launches)
+                                  int32_t *stage, int excl_sms, cudaStream_t s, int *launches)
 {
-    return launch_perm_serial(0, M, R, seeds, perms, stage, s, launches);
+    return launch_perm_serial(0, M, R, seeds, perms, stage, excl_sms, s, launches);
 }
 
 // ---------------------------------------------------------------------------

@@ -1,5 +1,5 @@
-"""GPU parity tests added in round 2: the thread-per-run bond-order generators and their
-bond orders generated under the sweep, validation of caller-supplied bond orders, claim-epoch rebasing,
+"""GPU parity tests added in round 2: the warp-per-run bond-order generators, bond orders
+generated under the sweep and on SMs of their own, validation of caller-supplied bond orders, claim-epoch rebasing,
 the 64-bit-record canonical kernels, more full-size runs, statistical validation of every
 generator at L = 256, and the measured floating-point error of every averaged column against
 an exact rational evaluation."""
@@ -116,6 +116,39 @@ def test_bond_orders_generated_under_the_sweep_are_exact(mode_name, pipeline):
             np.testing.assert_allclose(got[2], want_canon[2], rtol=1e-9,
                                        atol=1e-9 * np.abs(want_canon[2]).max())
         ctx.close()
+
+
+@pytest.mark.parametrize("mode_name", ["PERM_MT19937", "PERM_PHILOX_FY"])
+def test_bond_orders_generated_on_their_own_sms_are_exact(mode_name):
+    """L = 256 (one sweep CTA per SM): from the second chunk on, the warp-per-run shuffles run on SMs
+    of their own while the previous chunk is swept on the others (capped grid).  Four chunks must
+    give exactly the sums of one batch swept from host-supplied orders."""
+    from pypercolate_b200 import lowering
+    from oracle import oracle
+    n = _native()
+    g = lowering.lowered_spanning_2d_grid(256)
+    M = g.num_edges
+    runs = 600
+    seeds = np.arange(runs, dtype=np.uint32) * 77 + 3
+    ps = np.linspace(0.45, 0.55, 5)
+    gen = oracle.numpy_permutation if mode_name == "PERM_MT19937" else oracle.philox_fy_permutation
+    perms = np.stack([gen(int(s), M) for s in seeds])
+    base = ctx_for(g)
+    base.set_ps(ps)
+    base.run_fused(runs, n.PERM_HOST, perms, n.FUSE_MICRO | n.FUSE_CANON)
+    want_acc, want_canon = base.micro_export(), base.canon_export()
+    base.close()
+    for gen_sms in (24, 0):
+        with env(PZ_CHUNK_BYTES=720000000, PZ_GEN_SMS=gen_sms):
+            ctx = ctx_for(g)
+            ctx.set_ps(ps)
+            ctx.run_fused(runs, getattr(n, mode_name), seeds, n.FUSE_MICRO | n.FUSE_CANON)
+            assert ctx.micro_runs == runs
+            assert np.array_equal(acc_totals(ctx.micro_export()), acc_totals(want_acc))
+            got = ctx.canon_export()
+            assert got[0] == want_canon[0] == runs
+            np.testing.assert_allclose(got[1], want_canon[1], rtol=1e-13)
+            ctx.close()
 
 
 def test_caller_supplied_bond_orders_are_validated():
