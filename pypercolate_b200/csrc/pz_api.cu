@@ -112,7 +112,7 @@ struct pz_ctx {
     DevBuf<int32_t> band_lo, band_hi, tband_lo, tband_hi, porder_dev, canon_flags;
     DevBuf<double> sf;                    // survival functions [num_p][M+1]
     DevBuf<int32_t> perm_stage;           // warp-per-run shuffles: one L2-resident staging row per warp
-    int gen_sms = 0;                      // SMs a warp-per-run shuffle keeps to itself next to a sweep (PZ_GEN_SMS; 0: shares them)
+    int gen_sms = 32;                     // SMs a warp-per-run shuffle keeps to itself next to a sweep (PZ_GEN_SMS; 0: shares them)
     DevBuf<uint32_t> validate_bits;       // caller-supplied orders: one bit per (run, bond) + flag word
     int *validate_host = nullptr;         // pinned copy of the flag word
     uint32_t epoch_start = 0x003fffffu;   // first claim epoch of a run (PZ_EPOCH_START: tests)
