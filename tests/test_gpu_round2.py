@@ -151,6 +151,27 @@ def test_bond_orders_generated_on_their_own_sms_are_exact(mode_name):
             ctx.close()
 
 
+@pytest.mark.parametrize("L,runs", [(256, 120), (182, 150)])
+def test_soak_rows_of_many_runs_against_the_oracle(L, runs):
+    """Every row of many full runs of the one-run-per-SM sweep (finder warps, tails, star merging)
+    against the oracle, on bond orders of the Philox generator: 15.7 M (L = 256) bit-exact rows."""
+    from pypercolate_b200 import lowering
+    from oracle import oracle
+    n = _native()
+    g = lowering.lowered_spanning_2d_grid(L)
+    N, M = g.num_nodes, g.num_edges
+    ctx = ctx_for(g)
+    seeds = (np.arange(runs, dtype=np.uint64) * 2246822519 % 2 ** 32).astype(np.uint32)
+    rows, perms = ctx.run_rows(runs, n.PERM_PHILOX, seeds, want_perms=True)
+    ctx.close()
+    for r in range(runs):
+        if r % 16 == 0:
+            assert np.array_equal(perms[r], oracle.philox_permutation(int(seeds[r]), M))
+        ref = oracle.sweep_rows(N, M, g.eu, g.ev, g.side_mask, False, perms[r])
+        for name in ("n", "has_spanning_cluster", "max_cluster_size", "moments"):
+            assert np.array_equal(rows[r][name], ref[name]), (L, r, name)
+
+
 def test_caller_supplied_bond_orders_are_validated():
     """PZ_PERM_HOST / PZ_PERM_DEVICE orders index the bond list on the device: an entry outside
     [0, M) or a repeated entry is an argument error, not undefined behaviour."""
