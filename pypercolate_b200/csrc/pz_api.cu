@@ -523,6 +523,8 @@ static int check_run_args(pz_ctx *c, int32_t R, int perm_mode, const void *perm_
     if ((perm_mode & PZ_SEEDS_ON_DEVICE) && base_mode < PZ_PERM_MT19937)
         return fail(PZ_ERR_ARG, "PZ_SEEDS_ON_DEVICE needs a device RNG mode");
     if (R > 0 && !perm_src && c->M > 0) return fail(PZ_ERR_ARG, "perm_src is NULL");
+    if (base_mode == PZ_PERM_PHILOX && (long long)c->M > (1ll << 24))
+        return fail(PZ_ERR_ARG, "PZ_PERM_PHILOX supports at most 2^24 bonds (use PZ_PERM_PHILOX_FY or PZ_PERM_MT19937)");
     return PZ_OK;
 }
 
@@ -609,6 +611,8 @@ int pz_make_perms(pz_ctx *c, int32_t R, int perm_mode, const uint32_t *seeds, in
         return fail(PZ_ERR_ARG, "pz_make_perms: perm_mode must be a device RNG mode");
     if (R < 0 || (R > 0 && (!seeds || !out))) return fail(PZ_ERR_ARG, "pz_make_perms: bad arguments");
     if (R == 0 || c->M == 0) return PZ_OK;
+    if (perm_mode == PZ_PERM_PHILOX && (long long)c->M > (1ll << 24))
+        return fail(PZ_ERR_ARG, "PZ_PERM_PHILOX supports at most 2^24 bonds (use PZ_PERM_PHILOX_FY or PZ_PERM_MT19937)");
     PZ_CUDA(cudaSetDevice(c->device));
     const size_t per_run = (size_t)c->M * 4;
     const size_t chunk = is_device ? (size_t)R
