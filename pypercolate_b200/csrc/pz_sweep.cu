@@ -697,7 +697,10 @@ __global__ void __launch_bounds__(32 * CTA_WARPS, 1) sweep_cta_kernel(SweepArgs 
 #ifndef PZ_FW_WARPS
 #define PZ_FW_WARPS 4
 #endif
-static constexpr int FW_MAIN_WARPS = 16, FW_FIND_WARPS = PZ_FW_WARPS;
+#ifndef PZ_FW_MAIN_WARPS
+#define PZ_FW_MAIN_WARPS 16
+#endif
+static constexpr int FW_MAIN_WARPS = PZ_FW_MAIN_WARPS, FW_FIND_WARPS = PZ_FW_WARPS;
 static constexpr int FW_MAIN = 32 * FW_MAIN_WARPS, FW_FIND = 32 * FW_FIND_WARPS, FW_ALL = FW_MAIN + FW_FIND;
 static constexpr int FW_BPT = FW_MAIN / FW_FIND;          // bonds per finder thread and batch
 
