@@ -194,8 +194,15 @@ def test_micro_accumulators_are_exact(kind, L, runs, force):
     np.testing.assert_allclose(var[0], fm.var(axis=0, ddof=1), rtol=RTOL, atol=ATOL)
     for k in range(5):
         np.testing.assert_allclose(mean[2 + k], fmom[:, :, k].mean(axis=0), rtol=1e-13)
-        # numpy's two-pass variance itself carries ~1e-16 * mean^2 / var of error
-        np.testing.assert_allclose(var[1 + k], fmom[:, :, k].var(axis=0, ddof=1), rtol=1e-8, atol=ATOL)
+        # The device value is the exact rational rounded once (tests/test_gpu_round2.py checks it
+        # against fractions); numpy's two-pass variance of the float64 data carries an error of
+        # about eps * mean^2 / var of its own, so that is what bounds the comparison -- 1e-10 where
+        # the data allow it
+        want = fmom[:, :, k].var(axis=0, ddof=1)
+        m_ = fmom[:, :, k].mean(axis=0)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            allowed = np.where(want > 0, RTOL + 32 * np.finfo(float).eps * (m_ * m_ + want) / want, 0.0)
+        assert np.all(np.abs(var[1 + k] - want) <= allowed * want + ATOL), k
         assert np.array_equal(var[1 + k] == 0, np.ptp(fmom[:, :, k], axis=0) == 0)
     # export / import round trip (the cross-GPU exchange)
     ctx.reset_accumulators()
@@ -248,7 +255,9 @@ def test_canonical_chain_matches_reference_golden(name):
         elif f.endswith('_m2'):
             # M2 is a sum of squared differences: absolute accuracy scales with mean^2
             scale = np.abs(ref_red[f.replace('_m2', '_mean')]).max() ** 2
-            np.testing.assert_allclose(red[f], ref_red[f], rtol=1e-9, atol=1e-13 * scale)
+            # (relative bar 1e-10; the absolute term covers columns whose runs agree to many digits,
+            # where the reference's own M2 is rounding noise: measured in tests/test_gpu_round2.py)
+            np.testing.assert_allclose(red[f], ref_red[f], rtol=RTOL, atol=1e-13 * scale)
     fin = hpc.finalize_canonical_averages(g.num_nodes, ps, red, float(d['alpha']))
     ref_fin = d['finalized'].view(np.dtype(hpc.finalized_canonical_averages_dtype(spanning)))
     for f in fin.dtype.names:
@@ -263,7 +272,7 @@ def test_canonical_chain_matches_reference_golden(name):
             mean_w = np.broadcast_to(ref_fin[base][..., None], want.shape)
             got = np.where(np.isnan(got), mean_g, got)
             want = np.where(np.isnan(want), mean_w, want)
-        np.testing.assert_allclose(got, want, rtol=1e-8, atol=1e-12 * scale, equal_nan=True)
+        np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-12 * scale, equal_nan=True)
     ctx.close()
 
 
@@ -454,7 +463,7 @@ def test_fused_hpc_batch_equals_reference_map_reduce():
     ref = d['reduced'].view(np.dtype(hpc.canonical_averages_dtype(True)))
     for f in got.dtype.names:
         scale = np.abs(ref[f.replace('_m2', '_mean')]).max() ** (2 if f.endswith('_m2') else 1)
-        np.testing.assert_allclose(got[f], ref[f], rtol=1e-9, atol=1e-13 * scale)
+        np.testing.assert_allclose(got[f], ref[f], rtol=RTOL, atol=1e-13 * scale)
 
 
 def test_device_micro_arrays_equal_host_evaluation():
@@ -517,7 +526,7 @@ def test_study_driver_equals_jugfile_pipeline(tmp_path):
         want = oracle.finalize_canonical_averages(g.num_nodes, ps, reduced, study.ALPHA_1SIGMA)
         assert got[L].dtype == np.dtype(hpc.finalized_canonical_averages_dtype(True))
         for f in got[L].dtype.names:
-            np.testing.assert_allclose(got[L][f], want[f], rtol=1e-9, atol=1e-12, err_msg=f)
+            np.testing.assert_allclose(got[L][f], want[f], rtol=RTOL, atol=1e-12, err_msg=f)
     with np.load(out) as z:
         assert sorted(z.files) == ['4', '8']
         assert np.array_equal(z['8'], got[8])
@@ -785,7 +794,7 @@ def test_alternative_launch_shapes_give_identical_results(env):
     assert got[0] == want_canon[0]
     if "PZ_CHUNK_BYTES" in env:      # chunking changes the association of the Chan merge
         np.testing.assert_allclose(got[1], want_canon[1], rtol=1e-13)
-        np.testing.assert_allclose(got[2], want_canon[2], rtol=1e-9, atol=1e-9 * np.abs(want_canon[2]).max())
+        np.testing.assert_allclose(got[2], want_canon[2], rtol=RTOL, atol=1e-9 * np.abs(want_canon[2]).max())
     else:
         assert np.array_equal(got[1], want_canon[1]) and np.array_equal(got[2], want_canon[2])
     assert_rows_equal(ctx.run_rows(6, n.PERM_PHILOX, seeds[:6]), want_rows)

@@ -113,7 +113,7 @@ def test_bond_orders_generated_under_the_sweep_are_exact(mode_name, pipeline):
             assert got[0] == want_canon[0] == runs
             # (the batches differ, hence the association of the Chan merge)
             np.testing.assert_allclose(got[1], want_canon[1], rtol=1e-13)
-            np.testing.assert_allclose(got[2], want_canon[2], rtol=1e-9,
+            np.testing.assert_allclose(got[2], want_canon[2], rtol=RTOL,
                                        atol=1e-9 * np.abs(want_canon[2]).max())
         ctx.close()
 

@@ -82,7 +82,7 @@ def test_reduce_finalize_chain_matches_reference(name):
     ref_fin = d['finalized'].view(np.dtype(hpc.finalized_canonical_averages_dtype(spanning)))
     for f in fin.dtype.names:
         scale = np.nanmax(np.abs(ref_fin[f])) if np.isfinite(ref_fin[f]).any() else 0.0
-        np.testing.assert_allclose(fin[f], ref_fin[f], rtol=1e-9, atol=1e-12 * scale,
+        np.testing.assert_allclose(fin[f], ref_fin[f], rtol=RTOL, atol=1e-12 * scale,
                                    equal_nan=True, err_msg=f)
 
 
