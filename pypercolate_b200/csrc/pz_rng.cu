@@ -326,17 +326,21 @@ static constexpr int FEISTEL_ROUNDS = 20;
 static constexpr int FE_THREADS = 256;
 static constexpr int FE_ITEMS = 8;             // positions per thread
 
+// (ROUNDS = FEISTEL_ROUNDS in production; the statistical tests also run deliberately weakened networks,
+// PZ_FEISTEL_ROUNDS, to show that they notice)
+template <int ROUNDS>
 __global__ void __launch_bounds__(FE_THREADS) perm_feistel_kernel(int32_t M, int32_t R,
                                                                   const uint32_t *seeds, int32_t *perms,
                                                                   int k_bits)
 {
+    constexpr int FEISTEL_ROUNDS = ROUNDS;
     __shared__ uint32_t keys[FEISTEL_ROUNDS];
     const int run = blockIdx.y;
-    if (threadIdx.x < FEISTEL_ROUNDS / 4) {
+    if (threadIdx.x < (FEISTEL_ROUNDS + 3) / 4) {
         uint32_t o[4];
         philox4x32_10(seeds[run], PHILOX_KEY1, (uint32_t)threadIdx.x, 0u, 0u, 3u, o);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) keys[4 * threadIdx.x + q] = o[q];
+        for (int q = 0; q < 4; ++q) if (4 * threadIdx.x + q < FEISTEL_ROUNDS) keys[4 * threadIdx.x + q] = o[q];
     }
     __syncthreads();
     uint32_t key[FEISTEL_ROUNDS];
@@ -388,7 +392,17 @@ cudaError_t launch_perm_feistel(int32_t M, int32_t R, const uint32_t *seeds, int
     for (int r0 = 0; r0 < R; r0 += 65535) {         // gridDim.y limit
         const int rn = R - r0 < 65535 ? R - r0 : 65535;
         dim3 grid((unsigned)((M + per_block - 1) / per_block), (unsigned)rn);
-        perm_feistel_kernel<<<grid, FE_THREADS, 0, s>>>(M, rn, seeds + r0, perms + (size_t)r0 * M, k);
+        // (read per call: a test hook, not a tuning knob)
+        const int rounds = getenv("PZ_FEISTEL_ROUNDS") ? atoi(getenv("PZ_FEISTEL_ROUNDS")) : FEISTEL_ROUNDS;
+        switch (rounds) {
+        case 2: perm_feistel_kernel<2><<<grid, FE_THREADS, 0, s>>>(M, rn, seeds + r0, perms + (size_t)r0 * M, k); break;
+        case 3: perm_feistel_kernel<3><<<grid, FE_THREADS, 0, s>>>(M, rn, seeds + r0, perms + (size_t)r0 * M, k); break;
+        case 4: perm_feistel_kernel<4><<<grid, FE_THREADS, 0, s>>>(M, rn, seeds + r0, perms + (size_t)r0 * M, k); break;
+        case 6: perm_feistel_kernel<6><<<grid, FE_THREADS, 0, s>>>(M, rn, seeds + r0, perms + (size_t)r0 * M, k); break;
+        case 8: perm_feistel_kernel<8><<<grid, FE_THREADS, 0, s>>>(M, rn, seeds + r0, perms + (size_t)r0 * M, k); break;
+        default:
+            perm_feistel_kernel<FEISTEL_ROUNDS><<<grid, FE_THREADS, 0, s>>>(M, rn, seeds + r0, perms + (size_t)r0 * M, k);
+        }
         *launches += 1;
     }
     return cudaGetLastError();

@@ -459,6 +459,25 @@ def _rel(a, b):
     return r
 
 
+def test_statistical_validation_notices_a_weak_feistel_network():
+    """The same statistics on deliberately weakened Feistel networks (test hook PZ_FEISTEL_ROUNDS;
+    the product uses 20 rounds).  Measured on B200, 1e4 runs against the reference stream
+    (scripts/gpu_feistel_rounds.py): rounds 20 / 8 / 6 / 4 / 3 / 2 give max |z| = 2.6 / 2.8 / 4.5 /
+    181 / 809 / 454 and mean z^2 = 1.2 / 1.0 / 2.4 / 5428 / 94717 / 47164 -- these observables
+    cannot tell 8 rounds from a uniform shuffle at this precision, six rounds sit on the
+    threshold, four are rejected by a factor of forty; the shipped network has five times the
+    rounds at which the test first notices."""
+    ref = _l256_statistics("PERM_MT19937")
+    for rounds, must_fail in ((4, True), (8, False)):
+        with env(PZ_FEISTEL_ROUNDS=rounds):
+            _STAT_CACHE.pop(("PERM_FEISTEL", 10000, False), None)
+            got = _l256_statistics("PERM_FEISTEL")
+        _STAT_CACHE.pop(("PERM_FEISTEL", 10000, False), None)
+        z = _z_scores(ref, got)
+        rejected = np.abs(z).max() >= 4.5 or np.mean(z * z) >= 2.5 or _ks_first_spanning(ref, got) >= 1.95
+        assert rejected == must_fail, (rounds, np.abs(z).max(), np.mean(z * z))
+
+
 @pytest.mark.parametrize("name", ["hpc_grid8", "hpc_grid32", "hpc_odd"])
 def test_measured_float_error_of_reduced_and_finalized_columns(name, capsys):
     """North-star bar: floats within 1e-10 relative of the reference.  For every _mean / _m2 /
